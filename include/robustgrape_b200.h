@@ -1,0 +1,152 @@
+/* robustgrape_b200.h -- C ABI of librobustgrape_b200.so
+ *
+ * Drop-in boundary for the GRAPE propagator hot path of RobustGRAPE.jl.  The reference
+ * has no FFI (it is pure Julia); these entry points are what a `ccall` shim would bind
+ * in place of the Julia functions cited on each declaration (paths relative to the
+ * reference repository).  julia/RobustGRAPEB200.jl holds that shim; INTEGRATION.md
+ * shows the binding.
+ *
+ * Conventions
+ *  - Column-major arrays everywhere; complex numbers are interleaved (re, im) doubles,
+ *    i.e. Julia `ComplexF64` / numpy complex128 memory layout.  Tensor index order is
+ *    exactly what the reference functions return.
+ *  - Every function returns 0 on success or a negative rg_status; nothing throws,
+ *    aborts or prints.  rg_last_error() gives a message for the last failure.
+ *  - The caller owns all host buffers.  The library owns contexts, device memory and
+ *    streams.  A context is bound to one CUDA device and may be used by one host thread
+ *    at a time.  Calls with host buffers are blocking.
+ *  - There is no CPU fallback: without a CUDA device rg_ctx_create fails.
+ */
+#ifndef ROBUSTGRAPE_B200_H
+#define ROBUSTGRAPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rg_status {
+    RG_OK = 0,
+    RG_ERR_INVALID = -1,      /* bad argument / shape */
+    RG_ERR_CUDA = -2,         /* CUDA runtime error (message in rg_last_error) */
+    RG_ERR_UNSUPPORTED = -3,  /* descriptor outside what the kernels implement */
+    RG_ERR_NORM = -4,         /* ||dt*H||_1 outside the supported range */
+    RG_ERR_NOMEM = -5
+} rg_status;
+
+/* ---- declarative operators -------------------------------------------------------
+ * The reference's H0 / Herror / target_unitary are opaque closures (src/Types.jl:13,35,55).
+ * Across the ABI they are term lists:  op = sum_t coef_t * prod_f factor_f * M_t.        */
+enum { RG_F_VAR = 0, RG_F_COS = 1, RG_F_SIN = 2, RG_F_EXPI = 3, RG_F_ERR = 4,
+       RG_F_ERR1P_M1 = 5, RG_F_TABLE = 6 };
+enum { RG_S_MAIN = 0, RG_S_ADD = 1, RG_S_NONE = 2 };
+enum { RG_OWNER_H0 = -1, RG_OWNER_TARGET = -2 };   /* owner >= 0: error source index */
+#define RG_MAX_FACTORS 4
+
+typedef struct rg_factor {
+    int32_t kind;     /* RG_F_*: VAR u; COS cos u; SIN sin u; EXPI exp(i u); ERR err;
+                         ERR1P_M1 fl(1+err)-1; TABLE table[time_step][index]              */
+    int32_t space;    /* RG_S_MAIN: x[index] at the current time step; RG_S_ADD: x_add[index] */
+    int32_t index;
+    int32_t reserved;
+    double scale;     /* u = scale * v + offset */
+    double offset;
+} rg_factor;
+
+typedef struct rg_term {
+    int32_t owner;            /* RG_OWNER_H0, RG_OWNER_TARGET or error-source index */
+    int32_t nfactors;
+    double coef_re, coef_im;
+    rg_factor factors[RG_MAX_FACTORS];
+    int32_t nnz;
+    int32_t reserved;
+    const int32_t* rows;      /* 0-based */
+    const int32_t* cols;
+    const double* vals;       /* nnz interleaved complex */
+} rg_term;
+
+/* Fields mirror UnitaryRobustGRAPEProblem / FidelityRobustGRAPEProblem (src/Types.jl:31-40,52-56). */
+typedef struct rg_problem_desc {
+    int32_t ndim, ntimes, nparam, nb_additional_param, nerr;
+    double t0, eps, eps2;
+    int32_t nterms;           /* H0 terms and error-source terms */
+    const rg_term* terms;
+    int32_t ntarget_terms;    /* target_unitary(x_add) terms; 0 for unitary-only problems */
+    const rg_term* target_terms;
+    const double* projector;  /* ndim x ndim real, column-major; may be NULL if ntarget_terms==0 */
+    int32_t ntable_cols;
+    const double* table;      /* ntimes x ntable_cols real, column-major; may be NULL */
+    int32_t hermitian;        /* 1: H0 + error terms Hermitian for real variables (unitary propagators) */
+} rg_problem_desc;
+
+typedef struct rg_ctx rg_ctx;
+typedef struct rg_problem rg_problem;
+
+int rg_ctx_create(rg_ctx** out, int device);
+void rg_ctx_destroy(rg_ctx* ctx);
+const char* rg_last_error(const rg_ctx* ctx);
+/* Use an external CUDA stream (cudaStream_t as void*) for the *_dev entry points; NULL = the context's own. */
+int rg_ctx_set_stream(rg_ctx* ctx, void* cuda_stream);
+/* Wait for everything enqueued on the context stream; reports deferred kernel-side errors (RG_ERR_NORM). */
+int rg_ctx_synchronize(rg_ctx* ctx);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+int64_t rg_ctx_launch_count(const rg_ctx* ctx);
+
+int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_problem** out);
+void rg_problem_destroy(rg_problem* prob);
+
+/* nx = nparam*ntimes + nb_additional_param.  X is (nx, B): one pulse per column, each ordered
+ * [x_1(t_1)..x_p(t_1), x_1(t_2).. ; x_add] (src/UnitaryCalculations.jl:21-26).                   */
+
+/* Batched calculate_fidelity_and_derivatives (src/FidelityCalculations.jl:19-119), host buffers.
+ * F (B), F_dx (nx,B), F_d2err (nerr,B), F_d2err_dx (nx,nerr,B).  Output pointers may be NULL.   */
+int rg_fidelity_and_derivatives_batch(rg_problem* prob, int32_t B, const double* X,
+                                      double* F, double* F_dx, double* F_d2err, double* F_d2err_dx);
+
+/* Batched calculate_common! without regularisation (src/FidelityCalculations.jl:174-184):
+ * cost = 1-F + sum_e c_e F_d2err[e]^2 ; grad = -F_dx + 2 sum_e c_e F_d2err[e] F_d2err_dx[:,e].
+ * err_coeff (nerr, host) may be NULL when nerr==0.  cost (B), grad (nx,B).                       */
+int rg_cost_and_grad_batch(rg_problem* prob, int32_t B, const double* X, const double* err_coeff,
+                           double* cost, double* grad);
+
+/* Same two calls with DEVICE buffers, enqueued on the context stream without synchronising
+ * (err_coeff stays a host pointer).  For pipelines that keep pulses resident in HBM.             */
+int rg_fidelity_and_derivatives_batch_dev(rg_problem* prob, int32_t B, const double* dX,
+                                          double* dF, double* dF_dx, double* dF_d2err, double* dF_d2err_dx);
+int rg_cost_and_grad_batch_dev(rg_problem* prob, int32_t B, const double* dX, const double* err_coeff,
+                               double* dcost, double* dgrad);
+
+/* calculate_unitary_and_derivatives (src/UnitaryCalculations.jl:20-155), one pulse, materialised:
+ * U (d,d), U_dx (d,d,p,N), U_dx_add (d,d,a), U_derr (d,d,e), U_derr_dx (d,d,p,N,e),
+ * U_derr_dx_add (d,d,a,e); complex interleaved.  Output pointers may be NULL.                    */
+int rg_unitary_and_derivatives(rg_problem* prob, const double* x, double* U, double* U_dx,
+                               double* U_dx_add, double* U_derr, double* U_derr_dx, double* U_derr_dx_add);
+
+/* calculate_interaction_error_operators (src/UnitaryCalculations.jl:180-204): O (d,d,N,e) complex. */
+int rg_interaction_error_operators(rg_problem* prob, const double* x, double* O);
+
+/* calculate_fidelity_response (src/FidelityCalculations.jl:246-280): R (nfreq, nerr).
+ * Frequencies [first, first+count) of `freqs` are evaluated (shard over ranks); R receives
+ * `count` rows per error source laid out (count, nerr).                                          */
+int rg_fidelity_response(rg_problem* prob, const double* x, const double* freqs, int32_t nfreq,
+                         int32_t first, int32_t count, double* R);
+
+/* calculate_fidelity_response_fft (src/FidelityCalculations.jl:306-343): R (N*os, nerr), freqs_out (N*os). */
+int rg_fidelity_response_fft(rg_problem* prob, const double* x, int32_t oversampling,
+                             double* R, double* freqs_out);
+
+/* calculate_expectation_values (src/FidelityCalculations.jl:368-390): out (N, nerr). */
+int rg_expectation_values(rg_problem* prob, const double* x, double* out);
+
+/* Pinned host allocation helpers so callers can stage X / grad without pageable-copy overhead. */
+int rg_host_alloc(void** ptr, uint64_t bytes);
+void rg_host_free(void* ptr);
+
+/* FP64 peak microbenchmarks (DFMA loop, DMMA m8n8k4 loop) on the context device: TFLOP/s. */
+int rg_measure_fp64_peak(rg_ctx* ctx, double seconds, double* dfma_tflops, double* dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBUSTGRAPE_B200_H */

@@ -1,0 +1,311 @@
+"""ctypes binding of librobustgrape_b200.so (include/robustgrape_b200.h).
+
+The product path fails loudly when the CUDA library is missing or no GPU is present:
+there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import descriptors as D
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "librobustgrape_b200.so"
+
+RG_OK, RG_ERR_INVALID, RG_ERR_CUDA, RG_ERR_UNSUPPORTED, RG_ERR_NORM, RG_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+MAX_FACTORS = 4
+
+
+class RGError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"librobustgrape_b200 error {code}: {msg}")
+        self.code = code
+
+
+class rg_factor(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("space", C.c_int32), ("index", C.c_int32), ("reserved", C.c_int32),
+                ("scale", C.c_double), ("offset", C.c_double)]
+
+
+class rg_term(C.Structure):
+    _fields_ = [("owner", C.c_int32), ("nfactors", C.c_int32), ("coef_re", C.c_double), ("coef_im", C.c_double),
+                ("factors", rg_factor * MAX_FACTORS), ("nnz", C.c_int32), ("reserved", C.c_int32),
+                ("rows", C.POINTER(C.c_int32)), ("cols", C.POINTER(C.c_int32)), ("vals", C.POINTER(C.c_double))]
+
+
+class rg_problem_desc(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("ntimes", C.c_int32), ("nparam", C.c_int32),
+                ("nb_additional_param", C.c_int32), ("nerr", C.c_int32),
+                ("t0", C.c_double), ("eps", C.c_double), ("eps2", C.c_double),
+                ("nterms", C.c_int32), ("terms", C.POINTER(rg_term)),
+                ("ntarget_terms", C.c_int32), ("target_terms", C.POINTER(rg_term)),
+                ("projector", C.POINTER(C.c_double)),
+                ("ntable_cols", C.c_int32), ("table", C.POINTER(C.c_double)),
+                ("hermitian", C.c_int32)]
+
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+# every symbol declared in include/robustgrape_b200.h, with its signature
+SIGNATURES = {
+    "rg_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "rg_ctx_destroy": (None, [_vp]),
+    "rg_last_error": (C.c_char_p, [_vp]),
+    "rg_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "rg_ctx_synchronize": (C.c_int, [_vp]),
+    "rg_ctx_launch_count": (C.c_int64, [_vp]),
+    "rg_problem_create": (C.c_int, [_vp, C.POINTER(rg_problem_desc), C.POINTER(_vp)]),
+    "rg_problem_destroy": (None, [_vp]),
+    "rg_fidelity_and_derivatives_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "rg_cost_and_grad_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "rg_fidelity_and_derivatives_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "rg_cost_and_grad_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "rg_unitary_and_derivatives": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_interaction_error_operators": (C.c_int, [_vp, _vp, _vp]),
+    "rg_fidelity_response": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "rg_fidelity_response_fft": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
+    "rg_expectation_values": (C.c_int, [_vp, _vp, _vp]),
+    "rg_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
+    "rg_host_free": (None, [_vp]),
+    "rg_measure_fp64_peak": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RGError(RG_ERR_CUDA, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class Context:
+    """One CUDA device (rg_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.rg_ctx_create(C.byref(h), int(device))
+        if rc != 0:
+            raise RGError(rc, (self.lib.rg_last_error(None) or b"").decode())
+        self.handle = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise RGError(rc, (self.lib.rg_last_error(self.handle) or b"").decode())
+
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.rg_ctx_set_stream(self.handle, _vp(cuda_stream)))
+
+    def synchronize(self):
+        self.check(self.lib.rg_ctx_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.rg_ctx_launch_count(self.handle))
+
+    def measure_fp64_peak(self, seconds=0.5):
+        a, b = C.c_double(), C.c_double()
+        self.check(self.lib.rg_measure_fp64_peak(self.handle, float(seconds), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.rg_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# --------------------------------------------------------------------------------------------
+def _terms_to_c(terms, keep):
+    arr = (rg_term * max(1, len(terms)))()
+    for i, t in enumerate(terms):
+        ct = arr[i]
+        ct.owner = int(t.owner)
+        ct.nfactors = len(t.factors)
+        ct.coef_re, ct.coef_im = float(np.real(t.coef)), float(np.imag(t.coef))
+        for j, f in enumerate(t.factors):
+            cf = ct.factors[j]
+            cf.kind, cf.space, cf.index = int(f.kind), int(f.space), int(f.index)
+            cf.scale, cf.offset = float(f.scale), float(f.offset)
+        rows = np.array([e[0] for e in t.entries], dtype=np.int32)
+        cols = np.array([e[1] for e in t.entries], dtype=np.int32)
+        vals = np.array([[e[2].real, e[2].imag] for e in t.entries], dtype=np.float64).reshape(-1)
+        keep += [rows, cols, vals]
+        ct.nnz = len(t.entries)
+        ct.rows = rows.ctypes.data_as(C.POINTER(C.c_int32))
+        ct.cols = cols.ctypes.data_as(C.POINTER(C.c_int32))
+        ct.vals = vals.ctypes.data_as(_dp)
+    return arr
+
+
+class DescriptorError(TypeError):
+    pass
+
+
+def _require_terms(obj, cls, what):
+    if not isinstance(obj, cls):
+        raise DescriptorError(
+            f"{what} must be a robustgrape_b200.descriptors.{cls.__name__} (a declarative term list): the CUDA path "
+            f"cannot call an opaque closure (got {type(obj).__name__})")
+    return obj
+
+
+class Problem:
+    """Device-resident problem (rg_problem) built from the reference-style problem structs."""
+
+    def __init__(self, problem, ctx=None):
+        from .types import FidelityRobustGRAPEProblem, UnitaryRobustGRAPEProblem
+        self.ctx = ctx or default_context()
+        if isinstance(problem, FidelityRobustGRAPEProblem):
+            up, fp = problem.unitary_problem, problem
+        elif isinstance(problem, UnitaryRobustGRAPEProblem):
+            up, fp = problem, None
+        else:
+            raise TypeError("expected a UnitaryRobustGRAPEProblem or FidelityRobustGRAPEProblem")
+        self.up, self.fp = up, fp
+        H0 = _require_terms(up.H0, D.TermHamiltonian, "H0")
+        if H0.ndim != up.ndim:
+            raise ValueError("H0.ndim does not match problem.ndim")
+        terms = list(H0.terms)
+        table = H0.table
+        for e, src in enumerate(up.error_sources):
+            He = _require_terms(src.Herror, D.TermErrorHamiltonian, f"error_sources[{e}].Herror")
+            for t in He.terms:
+                terms.append(D.Term(t.coef, t.factors, t.entries, e))
+            if He.table is not None:
+                if table is not None and He.table is not table:
+                    raise ValueError("H0 and error sources must share one per-step table")
+                table = He.table
+        herm = H0.is_hermitian() and all(s.Herror.is_hermitian() for s in up.error_sources)
+        self._keep = []
+        desc = rg_problem_desc()
+        desc.ndim, desc.ntimes = int(up.ndim), int(up.ntimes)
+        desc.nb_additional_param, desc.nerr = int(up.nb_additional_param), len(up.error_sources)
+        nmain = 1 + max([f.index for t in terms for f in t.factors if f.space == D.S_MAIN and f.kind <= D.F_EXPI] + [-1])
+        self.nparam_min = nmain
+        desc.nparam = -1     # filled in per call (nparam is implied by len(x) in the reference)
+        desc.t0, desc.eps, desc.eps2 = float(up.t0), float(up.eps), float(up.eps2)
+        self._terms = _terms_to_c(terms, self._keep)
+        desc.nterms, desc.terms = len(terms), self._terms
+        if fp is not None:
+            tgt = _require_terms(fp.target_unitary, D.TermTarget, "target_unitary")
+            tterms = [D.Term(t.coef, t.factors, t.entries, D.OWNER_TARGET) for t in tgt.terms]
+            self._tterms = _terms_to_c(tterms, self._keep)
+            desc.ntarget_terms, desc.target_terms = len(tterms), self._tterms
+            proj = np.asfortranarray(np.asarray(fp.projector, dtype=np.float64))
+            if proj.shape != (up.ndim, up.ndim):
+                raise ValueError("projector must be ndim x ndim")
+            self._keep.append(proj)
+            desc.projector = proj.ctypes.data_as(_dp)
+        if table is not None:
+            tab = np.asfortranarray(np.asarray(table, dtype=np.float64))
+            if tab.shape[0] != up.ntimes:
+                raise ValueError("table must have ntimes rows")
+            self._keep.append(tab)
+            desc.ntable_cols, desc.table = tab.shape[1], tab.ctypes.data_as(_dp)
+        desc.hermitian = 1 if herm else 0
+        self._desc = desc
+        self._handles = {}     # nparam -> rg_problem*
+        self.ndim, self.ntimes = int(up.ndim), int(up.ntimes)
+        self.na, self.nerr = int(up.nb_additional_param), len(up.error_sources)
+
+    # nparam is not a field of the reference structs: it is derived from len(x) at call time
+    # (src/UnitaryCalculations.jl:21-25), so device problems are cached per nparam.
+    def handle_for(self, nx):
+        nmain = nx - self.na
+        if nmain < 0 or nmain % self.ntimes != 0:
+            raise AssertionError("Control parameter size must be a multiple of time steps")
+        p = nmain // self.ntimes
+        if p not in self._handles:
+            if p < self.nparam_min:
+                raise ValueError(f"H0 references x[{self.nparam_min - 1}] but only {p} control parameters per step were given")
+            self._desc.nparam = p
+            h = _vp()
+            self.ctx.check(self.ctx.lib.rg_problem_create(self.ctx.handle, C.byref(self._desc), C.byref(h)))
+            self._handles[p] = h
+        return self._handles[p], p
+
+    def close(self):
+        for h in self._handles.values():
+            self.ctx.lib.rg_problem_destroy(h)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+    # ---- batched hot path -------------------------------------------------------------------
+    def _batch_in(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        X = np.asfortranarray(X)
+        return X, X.shape[0], X.shape[1]
+
+    def fidelity_and_derivatives_batch(self, X, want_grad=True):
+        """X: (nx, B).  Returns F (B), F_dx (nx,B), F_d2err (nerr,B), F_d2err_dx (nx,nerr,B)."""
+        X, nx, B = self._batch_in(X)
+        h, p = self.handle_for(nx)
+        F = np.zeros(B)
+        F2 = np.zeros((self.nerr, B), order="F")
+        Fdx = np.zeros((nx, B), order="F") if want_grad else None
+        F2dx = np.zeros((nx, self.nerr, B), order="F") if want_grad else None
+        self.ctx.check(self.ctx.lib.rg_fidelity_and_derivatives_batch(h, B, _ptr(X), _ptr(F), _ptr(Fdx), _ptr(F2), _ptr(F2dx)))
+        return F, Fdx, F2, F2dx
+
+    def cost_and_grad_batch(self, X, error_source_coeff=()):
+        X, nx, B = self._batch_in(X)
+        h, p = self.handle_for(nx)
+        coeff = np.asarray(error_source_coeff, dtype=np.float64)
+        if len(coeff) != self.nerr:
+            raise AssertionError("error_source_coeff must have one entry per error source")
+        cost = np.zeros(B)
+        grad = np.zeros((nx, B), order="F")
+        self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch(h, B, _ptr(X), _ptr(coeff) if self.nerr else None, _ptr(cost), _ptr(grad)))
+        return cost, grad
+
+    def cost_and_grad_batch_dev(self, B, nx, dX_ptr, error_source_coeff, dcost_ptr, dgrad_ptr):
+        """Device-pointer variant (integers from e.g. torch.Tensor.data_ptr()); asynchronous."""
+        h, p = self.handle_for(nx)
+        coeff = np.asarray(error_source_coeff, dtype=np.float64)
+        self._keep_coeff = coeff
+        self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch_dev(h, B, _vp(dX_ptr), _ptr(coeff) if self.nerr else None,
+                                                             _vp(dcost_ptr), _vp(dgrad_ptr)))

@@ -1,0 +1,132 @@
+// rg_common.cuh -- device-side problem description, complex helpers and the
+// finite-difference coefficient algebra shared by all kernels.
+//
+// Semantics follow the reference's finite-difference formulas
+// (src/UnitaryCalculations.jl:45-97): the perturbed input is fl(x + eps) and the quotient
+// divides by the nominal eps.  Differences of coefficients are formed analytically
+// (e^{i(u+h)} - e^{iu} = e^{iu}(e^{ih} - 1), ...) so that no cancellation is amplified by 1/eps.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/robustgrape_b200.h"
+
+#define RG_MAX_VARS 8     // perturbation variables handled per problem (main + dependent additional)
+#define RG_MAX_ERR 4
+#define RG_MAX_ADD 8
+#define RG_MAX_MAIN 8
+
+typedef double2 cplx;
+
+struct DevFactor { int kind, space, index, pad; double scale, offset; };
+struct DevTerm { int owner, nf; double cr, ci; DevFactor f[RG_MAX_FACTORS]; };
+struct DevEntry { int row, col, term, pad; double vr, vi; };
+
+struct DevProblem {
+    int d, N, p, a, e;
+    double t0, dt, eps, eps2, inv_eps, inv_eps2sq;
+    int nterms; const DevTerm* terms;
+    int nent; const DevEntry* ents; const int* colptr;          // H0 + error entries, sorted by column
+    int ntt; const DevTerm* tterms; int ntent; const DevEntry* tents; const int* tcolptr;   // target
+    const double* PP;    // P0 * P      (d x d, column-major, real)
+    const double* PPt;   // (P0 * P)^T
+    const double* Pm;    // P = (P0 != 0)
+    double Dtr;          // tr(P0)
+    int nvar;            // perturbation variables: main 0..p-1, then additional params H depends on
+    int var_space[RG_MAX_VARS], var_index[RG_MAX_VARS];
+    int add_var[RG_MAX_ADD];   // index into vars for each additional parameter, or -1
+    int ntab; const double* table;
+    int hermitian;
+    int nx;              // p*N + a
+    int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
+};
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ cplx cmk(double x, double y) { return make_double2(x, y); }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return cmk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cmk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cscale(cplx a, double s) { return cmk(a.x * s, a.y * s); }
+__device__ __forceinline__ cplx cconj(cplx a) { return cmk(a.x, -a.y); }
+// acc += a*b  (4 DFMA)
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+__device__ __forceinline__ void cfma_conj(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+
+// ---------------------------------------------------------------------------------------
+// Factor value and accurate finite difference.
+//   value  f(v)           (err factors use `errv`)
+//   delta  f(v + h) - f(v) when the factor depends on the perturbed variable (pspace, pindex)
+// h is the step actually taken in the variable, fl(v + eps) - v.
+struct EvalCtx {
+    const double* xk;      // main parameters at this step (p)
+    const double* xadd;    // additional parameters (a)
+    double errv;           // error amplitude seen by ERR factors
+    const double* table; int N; int k;   // per-step table, 0-based step
+};
+
+__device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int pspace, int pindex, double h,
+                                   cplx& val, cplx& del) {
+    del = cmk(0.0, 0.0);
+    switch (f.kind) {
+    case RG_F_ERR: val = cmk(c.errv, 0.0); return;
+    case RG_F_ERR1P_M1: val = cmk((1.0 + c.errv) - 1.0, 0.0); return;
+    case RG_F_TABLE: val = cmk(c.table[(size_t)f.index * c.N + c.k], 0.0); return;
+    default: break;
+    }
+    const double v = (f.space == RG_S_MAIN) ? c.xk[f.index] : c.xadd[f.index];
+    const bool plain = (f.scale == 1.0 && f.offset == 0.0);
+    const double u = plain ? v : fma(f.scale, v, f.offset);
+    const bool dep = (f.space == pspace && f.index == pindex);
+    const double hu = dep ? f.scale * h : 0.0;
+    if (f.kind == RG_F_VAR) { val = cmk(u, 0.0); del = cmk(hu, 0.0); return; }
+    double s, co;
+    sincos(u, &s, &co);
+    double sh = 0.0, s2 = 0.0;      // sin(hu), sin(hu/2)
+    if (dep) { sh = sin(hu); s2 = sin(0.5 * hu); }
+    // e^{ihu} - 1 = -2 sin^2(hu/2) + i sin(hu)
+    const double er = -2.0 * s2 * s2, ei = sh;
+    if (f.kind == RG_F_EXPI) {
+        val = cmk(co, s);
+        del = cmk(co * er - s * ei, co * ei + s * er);
+    } else if (f.kind == RG_F_COS) {
+        val = cmk(co, 0.0);
+        del = cmk(co * er - s * ei, 0.0);          // Re(e^{iu}(e^{ih}-1))
+    } else {                                        // RG_F_SIN
+        val = cmk(s, 0.0);
+        del = cmk(co * ei + s * er, 0.0);          // Im(e^{iu}(e^{ih}-1))
+    }
+}
+
+// Term coefficient and its finite difference in variable (pspace,pindex) with step h:
+//   base = coef * prod f ;  delta = coef * (prod f(v+h) - prod f(v))   by telescoping.
+__device__ inline void term_coef(const DevTerm& t, const EvalCtx& c, int pspace, int pindex, double h,
+                                 cplx& base, cplx& delta) {
+    cplx P = cmk(t.cr, t.ci), Dl = cmk(0.0, 0.0);
+    for (int i = 0; i < t.nf; ++i) {
+        cplx v, dv;
+        factor_eval(t.f[i], c, pspace, pindex, h, v, dv);
+        // Dl' = Dl * (v + dv) + P * dv ;  P' = P * v
+        Dl = cadd(cmul(Dl, cadd(v, dv)), cmul(P, dv));
+        P = cmul(P, v);
+    }
+    base = P; delta = Dl;
+}
+
+// Taylor degree for ||A||_1 <= theta with remainder below 2^-53 (expm section).
+__device__ __forceinline__ int taylor_degree(double nrm) {
+    if (nrm <= 1.5e-3) return 4;
+    if (nrm <= 1.6e-2) return 6;
+    if (nrm <= 6.5e-2) return 8;
+    if (nrm <= 0.16) return 10;
+    if (nrm <= 0.31) return 12;
+    if (nrm <= 0.52) return 14;
+    if (nrm <= 0.78) return 16;
+    if (nrm <= 1.10) return 18;
+    return 99;   // needs scaling and squaring
+}
