@@ -93,6 +93,12 @@ int rg_ctx_synchronize(rg_ctx* ctx);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t rg_ctx_launch_count(const rg_ctx* ctx);
 
+/* Per-kernel timing with CUDA events on the launch stream (bench.py's live roofline).
+ * Kernel classes: 0 step propagators (k_steps), 1 mixed second differences (k_steps_so), 2 chunk scan,
+ * 3 fidelity-gradient sweep, 4 sensitivity-gradient sweep, 5 epilogues, 6 analysis kernels.          */
+int rg_ctx_set_timing(rg_ctx* ctx, int enable);
+int rg_ctx_get_timing(rg_ctx* ctx, int kernel, int reset, double* ms, int64_t* count);
+
 int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_problem** out);
 void rg_problem_destroy(rg_problem* prob);
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "rg_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "rg_ctx_synchronize": (C.c_int, [_vp]),
     "rg_ctx_launch_count": (C.c_int64, [_vp]),
+    "rg_ctx_set_timing": (C.c_int, [_vp, C.c_int]),
+    "rg_ctx_get_timing": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(C.c_int64)]),
     "rg_problem_create": (C.c_int, [_vp, C.POINTER(rg_problem_desc), C.POINTER(_vp)]),
     "rg_problem_destroy": (None, [_vp]),
     "rg_fidelity_and_derivatives_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
@@ -123,6 +125,20 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.rg_ctx_launch_count(self.handle))
+
+    KERNELS = ("k_steps", "k_steps_so", "k_scan", "k_grad", "k_grad_err", "epilogue", "analysis")
+
+    def set_timing(self, enable):
+        self.check(self.lib.rg_ctx_set_timing(self.handle, 1 if enable else 0))
+
+    def get_timing(self, reset=True):
+        """{kernel class: (total ms, launches)} measured with CUDA events on the launch stream."""
+        out = {}
+        for i, name in enumerate(self.KERNELS):
+            ms, n = C.c_double(), C.c_int64()
+            self.check(self.lib.rg_ctx_get_timing(self.handle, i, 1 if reset else 0, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
 
     def measure_fp64_peak(self, seconds=0.5):
         a, b = C.c_double(), C.c_double()

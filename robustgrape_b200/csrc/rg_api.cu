@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+enum { RG_K_STEPS = 0, RG_K_STEPS_SO = 1, RG_K_SCAN = 2, RG_K_GRAD = 3, RG_K_GRAD_ERR = 4, RG_K_EPILOGUE = 5, RG_K_ANALYSIS = 6, RG_NKERNELS = 8 };
 #include "rg_smalld.cuh"
 #include "rg_analysis.cuh"
 #include "rg_peak.cuh"
@@ -22,6 +23,23 @@ struct rg_ctx {
     int* h_status = nullptr;    // pinned
     int sm_count = 148;
     size_t ws_limit = (size_t)64 << 30;
+    // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
+    bool timing = false;
+    struct Span { int kernel; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    double kern_ms[RG_NKERNELS] = {0};
+    int64_t kern_n[RG_NKERNELS] = {0};
+};
+
+struct KTimer {
+    rg_ctx* c; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KTimer(rg_ctx* c_, int k_) : c(c_), k(k_) {
+        if (c->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    }
+    ~KTimer() {
+        c->launches++;
+        if (c->timing) { cudaEventRecord(e1, c->stream); c->spans.push_back({k, e0, e1}); }
+    }
 };
 
 struct DevBuf {
@@ -128,6 +146,30 @@ extern "C" int rg_ctx_synchronize(rg_ctx* c) {
         cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
         RG_FAIL(c, RG_ERR_NORM, "||dt*H||_1 exceeds the range of the Taylor propagator (1.1); reduce dt");
     }
+    return RG_OK;
+}
+
+// Per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the launch stream.
+extern "C" int rg_ctx_set_timing(rg_ctx* c, int enable) {
+    if (!c) return RG_ERR_INVALID;
+    c->timing = enable != 0;
+    return RG_OK;
+}
+// Collect finished spans (synchronises the stream); returns accumulated milliseconds and launch count
+// for kernel class `kernel` (RG_K_*), and clears them when `reset` is set.
+extern "C" int rg_ctx_get_timing(rg_ctx* c, int kernel, int reset, double* ms, int64_t* count) {
+    if (!c || kernel < 0 || kernel >= RG_NKERNELS) return RG_ERR_INVALID;
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (auto& s : c->spans) {
+        float t = 0;
+        cudaEventElapsedTime(&t, s.e0, s.e1);
+        c->kern_ms[s.kernel] += t; c->kern_n[s.kernel]++;
+        cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
+    }
+    c->spans.clear();
+    if (ms) *ms = c->kern_ms[kernel];
+    if (count) *count = c->kern_n[kernel];
+    if (reset) { c->kern_ms[kernel] = 0; c->kern_n[kernel] = 0; }
     return RG_OK;
 }
 
@@ -364,9 +406,9 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         if (rc) return rc;
         const long long items = (long long)B * nc;
         const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_STEPS);
         k_steps<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
                                                 pr->Wlb.as<cplx>(), ctx->d_status);
-        ctx->launches++;
     }
     // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
     if (ne > 0 && want_grad && P.nvar > 0) {
@@ -378,8 +420,8 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         if (rc) return rc;
         const long long items = (long long)B * P.N;
         const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_STEPS_SO);
         k_steps_so<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, pr->ws.as<cplx>(), ctx->d_status);
-        ctx->launches++;
     }
     // ---- K2
     {
@@ -390,10 +432,10 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         int rc = set_smem(ctx, k_scan<D>, smem);
         if (rc) return rc;
         dim3 grid((B + wpc * G - 1) / (wpc * G), 1 + ne);
+        KTimer kt(ctx, RG_K_SCAN);
         k_scan<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, nc, pr->Qb.as<cplx>(), pr->Wlb.as<cplx>(), pr->Cb.as<cplx>(),
                                                pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(),
                                                iF, iF2, pr->addT.as<double>());
-        ctx->launches++;
     }
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     // mode 1 with no error sources writes -F_dx straight into grad
@@ -409,10 +451,10 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             int rc = set_smem(ctx, k_grad<D, false>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), 1);
+            KTimer kt(ctx, RG_K_GRAD);
             k_grad<D, false><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
-            ctx->launches++;
         }
         if (ne > 0) {
             const int gs = k3_group_stride(D, 2 + 2 * P.nvar);
@@ -422,19 +464,20 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             int rc = set_smem(ctx, k_grad<D, true>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), ne);
+            KTimer kt(ctx, RG_K_GRAD_ERR);
             k_grad<D, true><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 0.0, iF2dx, pr->addS.as<double>());
-            ctx->launches++;
         }
         // ---- K4: additional parameters
         if (P.a > 0) {
             const int n = B * (1 + ne) * P.a;
+            KTimer kt(ctx, RG_K_EPILOGUE);
             k_add_params<<<(n + 127) / 128, 128, 0, st>>>(P, B, pr->addT.as<double>(), pr->addS.as<double>(), iFdx, sign0, iF2dx);
-            ctx->launches++;
         }
     }
     if (mode == 1) {
+        KTimer kt(ctx, RG_K_EPILOGUE);
         if (ne > 0 && want_grad) {
             const size_t n = (size_t)B * P.nx;
             const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
@@ -444,7 +487,6 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         } else {
             k_cost_only<<<(B + 255) / 256, 256, 0, st>>>(B, iF, dF);
         }
-        ctx->launches++;
     }
     CU(ctx, cudaGetLastError());
     return RG_OK;

@@ -323,7 +323,7 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
         assemble_col<D>(P.ents, P.colptr, coef, mA, l, ghost);
         double nrm = 0.0;
 #pragma unroll
-        for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += fabs(a.x) + fabs(a.y); }
+        for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
         int m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
         m = __reduce_max_sync(amask, m);
         if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }
@@ -456,7 +456,7 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     assemble_col<D>(P.ents, P.colptr, coef, mA, l);
     double nrm = 0.0;
 #pragma unroll
-    for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += fabs(a.x) + fabs(a.y); }
+    for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
     int m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
     m = __reduce_max_sync(amask, m);
     if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }

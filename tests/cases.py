@@ -1,0 +1,92 @@
+"""Problem definitions shared by the tests and the golden-fixture generator."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+import robustgrape_b200 as rg
+from robustgrape_b200 import rydberg_tools as rt
+from robustgrape_b200.descriptors import (Factor, Term, TermHamiltonian, TermErrorHamiltonian, TermTarget,
+                                          S_MAIN, S_ADD, OWNER_H0, OWNER_TARGET)
+
+PROJ5 = np.diag([1.0, 2.0, 1.0, 0.0, 0.0])
+PROJ7 = np.diag([1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0])
+
+
+def cz_problem(ntimes, t0, errors=(), model="symmetric_blockaded", eps=0.0, delta=0.0):
+    """The CZ problems of reference test/runtests.jl and examples/*.jl, with descriptor closures."""
+    srcs = []
+    for i, e in enumerate(errors):
+        if e == "amp":
+            srcs.append(rg.ErrorSource(rt.rydberg_amplitude_error(model, source=i)))
+        elif e in ("freq", "decay"):
+            srcs.append(rg.ErrorSource(rt.rydberg_frequency_error(model, source=i)))
+        else:
+            raise ValueError(e)
+    d = 5 if model == "symmetric_blockaded" else 7
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=d, H0=rt.rydberg_h0(model, eps=eps, delta=delta),
+                                      nb_additional_param=1, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, PROJ5 if d == 5 else PROJ7, rt.cz_target(model))
+
+
+def cz_problem_closures(ntimes, t0, errors=()):
+    """Same problem with plain Python closures calling the literal builders (the reference's style)."""
+    H0 = lambda k, phi, xa: rt.rydberg_hamiltonian_symmetric_blockaded(phi[0], 0, 0)
+    srcs = []
+    for e in errors:
+        if e == "amp":
+            srcs.append(rg.ErrorSource(lambda k, phi, xa, err: rt.rydberg_hamiltonian_symmetric_blockaded(phi[0], err, 0) - H0(k, phi, xa)))
+        else:
+            srcs.append(rg.ErrorSource(lambda k, phi, xa, err: rt.rydberg_hamiltonian_symmetric_blockaded(phi[0], 0, err) - H0(k, phi, xa)))
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=5, H0=H0, nb_additional_param=1, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, PROJ5, lambda xa: rt.cz_with_1q_phase_symmetric(xa[0]))
+
+
+def detuned_problem(ntimes, t0, errors=("amp",)):
+    """A problem whose Hamiltonian depends on an additional parameter: two controls per step
+    (phase phi = x[0], amplitude scale via cos(x[1])), detuning = x_add[1], target phase = x_add[0],
+    plus a per-step envelope table.  Exercises VAR/COS/TABLE factors, p=2, a=2 and dH/dx_add != 0."""
+    up_ent = ((1, 3, 0.5), (2, 4, 1 / math.sqrt(2.0)))
+    dn_ent = tuple((c, r, v) for r, c, v in up_ent)
+    env = 0.8 + 0.2 * np.cos(np.linspace(0, 2.0, ntimes))[:, None]
+    terms = [
+        Term(1.0, (Factor.expi(S_MAIN, 0, -1.0), Factor.cos(S_MAIN, 1, 0.5, 0.1), Factor.table(0)), up_ent, OWNER_H0),
+        Term(1.0, (Factor.expi(S_MAIN, 0, +1.0), Factor.cos(S_MAIN, 1, 0.5, 0.1), Factor.table(0)), dn_ent, OWNER_H0),
+        Term(1.0, (Factor.var(S_ADD, 1, 0.3, 0.05),), ((3, 3, 1.0), (4, 4, 1.0)), OWNER_H0),
+    ]
+    H0 = TermHamiltonian(5, terms, table=env)
+    srcs = []
+    for i, e in enumerate(errors):
+        if e == "amp":
+            eterms = [
+                Term(1.0, (Factor.expi(S_MAIN, 0, -1.0), Factor.cos(S_MAIN, 1, 0.5, 0.1), Factor.table(0), Factor.err1p_m1()), up_ent, i),
+                Term(1.0, (Factor.expi(S_MAIN, 0, +1.0), Factor.cos(S_MAIN, 1, 0.5, 0.1), Factor.table(0), Factor.err1p_m1()), dn_ent, i),
+            ]
+            srcs.append(rg.ErrorSource(TermErrorHamiltonian(5, eterms, table=env)))
+        else:
+            srcs.append(rg.ErrorSource(TermErrorHamiltonian(5, [Term(1.0, (Factor.err(), Factor.sin(S_ADD, 1, 1.0, 0.7)),
+                                                                      ((3, 3, 1.0), (4, 4, 1.0)), i)], table=env)))
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=5, H0=H0, nb_additional_param=2, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, PROJ5, rt.cz_target("symmetric_blockaded"))
+
+
+def random_pulse(fp, nparam=1, seed=0):
+    up = fp.unitary_problem
+    rng = np.random.default_rng(seed)
+    return 2 * np.pi * rng.random(nparam * up.ntimes + up.nb_additional_param)
+
+
+def golden_cases():
+    cases = {}
+    fp = cz_problem(24, 7.613 * 24 / 200)
+    cases["cz5_e0_N24"] = (fp, random_pulse(fp, 1, 11))
+    fp = cz_problem(17, 14.32 * 17 / 200, ("amp",))
+    cases["cz5_e1_N17"] = (fp, random_pulse(fp, 1, 12))
+    fp = cz_problem(12, 7.613 * 12 / 100, ("amp", "freq"))
+    cases["cz5_e2_N12"] = (fp, random_pulse(fp, 1, 13))
+    fp = cz_problem(10, 7.613 * 10 / 100, ("amp", "freq"), model="full_blockaded")
+    cases["cz7_e2_N10"] = (fp, random_pulse(fp, 1, 14))
+    fp = detuned_problem(9, 1.1, ("amp", "freq"))
+    cases["detuned_p2_a2_e2_N9"] = (fp, random_pulse(fp, 2, 15))
+    return cases

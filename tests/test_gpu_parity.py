@@ -1,0 +1,175 @@
+"""Parity of the CUDA path (called through the C ABI) against the oracles.
+
+Tolerances (stated per check):
+  * vs the exact-semantics golden fixtures (mpmath, tests/golden/): 1e-10 relative to the largest
+    component of each output -- the north-star tolerance.  The CUDA path forms differenced
+    exponentials, so it sits ~1e-15 from the exact value of the reference's finite-difference formulas.
+  * vs the FP64 literal restatement (numpy / C++ port): F at 1e-12; derivative outputs at 2e-5 of the
+    largest component, which is the restatement's own finite-difference noise floor (measured in
+    tests/test_oracle_structure.py::test_fp64_restatement_vs_exact_semantics_noise_floor).
+"""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import robustgrape_b200 as rg
+from robustgrape_b200 import _lib
+from cases import cz_problem, detuned_problem, golden_cases, random_pulse
+from oracle import cpu_port, reference_oracle as ro
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+NAMES = ["F", "F_dx", "F_d2err", "F_d2err_dx"]
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if b.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("name", list(golden_cases().keys()))
+def test_golden_exact_semantics(gpu_ctx, name):
+    fp, x = golden_cases()[name]
+    z = np.load(GOLD / f"{name}.npz")
+    got = rg.calculate_fidelity_and_derivatives(fp, z["x"])
+    for k, g in zip(NAMES, got):
+        assert relmax(g, z["exact_" + k]) < 1e-10, (name, k, relmax(g, z["exact_" + k]))
+
+
+def test_known_answer_evered_pulse(gpu_ctx):
+    """reference test/runtests.jl:115-165."""
+    T0 = 2 * np.pi * 1.22
+    A, w0, p0, d0, th = 0.7701624, 0.97525275, -0.97449603, -0.04319765, 2.0802725844516097
+    times = np.linspace(0, T0, 1000)
+    xs = np.concatenate([A * np.cos(w0 * times - p0) + d0 * times, [th]])
+    F = rg.calculate_fidelity_and_derivatives(cz_problem(1000, T0), xs)[0]
+    assert F > 0.9999
+    assert abs(F - 0.9999961847609591) < 1e-12
+
+
+@pytest.mark.parametrize("N,errors,model,B", [
+    (1, (), "symmetric_blockaded", 1), (2, ("amp",), "symmetric_blockaded", 3), (3, ("freq", "amp"), "symmetric_blockaded", 2),
+    (33, (), "symmetric_blockaded", 7), (50, ("amp",), "symmetric_blockaded", 5), (64, ("amp", "freq"), "symmetric_blockaded", 4),
+    (200, ("amp",), "symmetric_blockaded", 37), (41, ("amp", "freq"), "full_blockaded", 6), (129, (), "full_blockaded", 9)])
+def test_batch_vs_fp64_restatement(gpu_ctx, N, errors, model, B):
+    """Seeded random pulses incl. ragged sizes (N not a multiple of the chunk length, N=1, odd batches)."""
+    fp = cz_problem(N, 7.613 * max(N, 10) / 500, errors, model)
+    rng = np.random.default_rng(100 + N)
+    X = 2 * np.pi * rng.random((N + 1, B))
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    pF, pFdx, pF2, pF2dx = cpu_port.PortProblem(fp).fidelity_and_derivatives_batch(X)
+    assert np.abs(F - pF).max() < 1e-12
+    assert relmax(Fdx, pFdx) < 2e-5
+    assert relmax(F2, pF2) < 2e-5
+    assert relmax(F2dx, pF2dx) < 2e-5
+    coeff = [1e-4, 3e-4][:len(errors)]
+    c, g = rg.cost_and_gradient_batch(fp, X, coeff)
+    pc, pg = cpu_port.PortProblem(fp).cost_and_grad_batch(X, coeff)
+    assert np.abs(c - pc).max() < 1e-9
+    assert relmax(g, pg) < 2e-5
+    # cost/grad epilogue is exactly the reference's combination of the four outputs (src/FidelityCalculations.jl:178-184)
+    c2 = 1 - F + sum(coeff[e] * F2[e] ** 2 for e in range(len(errors)))
+    g2 = -Fdx + sum(2 * coeff[e] * F2[e][None, :] * F2dx[:, e, :] for e in range(len(errors)))
+    assert np.abs(c - c2).max() < 1e-14 and np.abs(g - g2).max() < 1e-13
+
+
+def test_additional_parameter_dependent_hamiltonian(gpu_ctx):
+    """p=2, a=2, table envelope, dH/dx_add != 0 (VAR/COS/SIN/TABLE factors)."""
+    fp = detuned_problem(23, 2.5, ("amp", "freq"))
+    X = np.stack([random_pulse(fp, 2, s) for s in range(4)], axis=1)
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    for b in range(4):
+        a = ro.calculate_fidelity_and_derivatives(fp, X[:, b])
+        assert abs(F[b] - a[0]) < 1e-12
+        assert relmax(Fdx[:, b], a[1]) < 2e-5
+        assert relmax(F2[:, b], a[2]) < 2e-5
+        assert relmax(F2dx[:, :, b], a[3]) < 2e-5
+
+
+def test_chunk_length_independence(gpu_ctx, monkeypatch):
+    """The time-parallel blocking must not change results beyond rounding: chunk lengths 1, 5, 32, N."""
+    N, B = 100, 6
+    X = 2 * np.pi * np.random.default_rng(3).random((N + 1, B))
+    ref = None
+    for L in (1, 5, 32, 100):
+        monkeypatch.setenv("RG_CHUNK", str(L))
+        fp = cz_problem(N, 3.0, ("amp",))
+        out = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+        if ref is None:
+            ref = out
+        else:
+            for k, u, v in zip(NAMES, out, ref):
+                assert relmax(u, v) < 1e-11, (L, k)
+
+
+def test_batch_composition_independence(gpu_ctx):
+    """Pulse b's result does not depend on which other pulses share the batch."""
+    N = 77
+    fp = cz_problem(N, 2.0, ("amp",))
+    X = 2 * np.pi * np.random.default_rng(8).random((N + 1, 10))
+    full = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    one = rg.calculate_fidelity_and_derivatives(fp, X[:, 4])
+    assert full[0][4] == one[0]
+    assert np.array_equal(full[1][:, 4], one[1])
+    assert np.array_equal(full[3][:, :, 4], one[3])
+
+
+def test_full_size_properties(gpu_ctx):
+    """BASELINE.json config C4 (8192 pulses x 1000 steps): size-independent properties.
+       * 0 <= F <= 1;
+       * rows match a 64-pulse oracle sample;
+       * the gradient of a handful of pulses matches a central difference of the GPU's own F;
+       * deterministic: two runs are bitwise identical."""
+    import bench
+    N, B = 1000, 8192
+    fp = bench.make_problem(N, 0)
+    X = bench.make_pulses(N, B).T
+    cost, grad = rg.cost_and_gradient_batch(fp, X)
+    cost2, grad2 = rg.cost_and_gradient_batch(fp, X)
+    assert np.array_equal(cost, cost2) and np.array_equal(grad, grad2)
+    assert np.all(cost >= -1e-12) and np.all(cost <= 1 + 1e-12)
+    idx = np.arange(0, B, 128)
+    pc, pg = cpu_port.PortProblem(fp).cost_and_grad_batch(X[:, idx])
+    assert np.abs(cost[idx] - pc).max() < 1e-11
+    assert relmax(grad[:, idx], pg) < 2e-5
+    h = 1e-5
+    for b, i in [(0, 0), (17, 500), (8191, 999), (4096, 1000)]:
+        xp, xm = X[:, b].copy(), X[:, b].copy()
+        xp[i] += h; xm[i] -= h
+        c2, _ = rg.cost_and_gradient_batch(fp, np.stack([xp, xm], axis=1))
+        assert abs((c2[0] - c2[1]) / (2 * h) - grad[i, b]) < 1e-7
+
+
+def test_api_shapes_and_asserts(gpu_ctx):
+    fp = cz_problem(10, 1.0, ("amp",))
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives(fp, np.linspace(0, 1, 11))
+    assert isinstance(F, float) and Fdx.shape == (11,) and F2.shape == (1,) and F2dx.shape == (11, 1)
+    with pytest.raises(AssertionError):                    # src/UnitaryCalculations.jl:22
+        rg.calculate_fidelity_and_derivatives(cz_problem(7, 1.0), np.zeros(12))
+    with pytest.raises(AssertionError):                    # src/FidelityCalculations.jl:162
+        rg.cost_and_gradient_batch(fp, np.zeros((11, 2)), [])
+
+
+def test_norm_out_of_range_is_reported(gpu_ctx):
+    fp = cz_problem(2, 40.0)        # dt * ||H|| ~ 14: outside the Taylor range
+    with pytest.raises(_lib.RGError) as ei:
+        rg.calculate_fidelity_and_derivatives(fp, np.zeros(3))
+    assert ei.value.code == _lib.RG_ERR_NORM
+
+
+def test_optimize_wrapper_reaches_high_fidelity(gpu_ctx):
+    """reference test/runtests.jl:356-416 through the GPU cost/gradient (scipy L-BFGS-B as optimiser)."""
+    N, T0 = 200, 2 * np.pi * 1.22
+    fp = cz_problem(N, T0)
+    rng = np.random.default_rng(42)
+    prm = rg.FidelityRobustGRAPEParameters(
+        x_initial=np.concatenate([2 * np.pi * 0.001 * rng.random(N), [2 * np.pi * rng.random()]]),
+        regularization_functions=[ro.runtests_regularization_cost_phase], regularization_coeff1=[1e-6],
+        regularization_coeff2=[1e-6], error_source_coeff=[], iterations=200,
+        additional_parameters={"f_abstol": 1e-15, "g_tol": 3e-10})
+    res = rg.optimize_fidelity_and_error_sources(fp, prm)
+    assert 1 - rg.calculate_fidelity_and_derivatives(fp, res.x)[0] < 1e-6

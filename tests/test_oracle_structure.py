@@ -1,0 +1,162 @@
+"""The oracle reproduces every test structure of the reference (test/runtests.jl), one for one.
+PARITY UNPINNED: the reference ships no golden vectors; these are the reference's own
+self-consistency checks (rtol = 1e-3) and its one RNG-free known answer."""
+import numpy as np
+import pytest
+
+import robustgrape_b200 as rg
+from cases import cz_problem, cz_problem_closures
+from oracle import cpu_port, exact_oracle as eo, reference_oracle as ro
+
+T0 = 2 * np.pi * 1.22
+
+
+def evered_pulse(n=1000):
+    """test/runtests.jl:126-140"""
+    A, w0, p0, d0, th = 0.7701624, 0.97525275, -0.97449603, -0.04319765, 2.0802725844516097
+    times = np.linspace(0, T0, n)
+    return np.concatenate([A * np.cos(w0 * times - p0) + d0 * times, [th]])
+
+
+def test_known_answer_time_optimal_cz():
+    """test/runtests.jl:115-165: F > 0.9999 (restatement value 0.9999961847609591)."""
+    xs = evered_pulse()
+    F = ro.calculate_fidelity_and_derivatives(cz_problem(1000, T0), xs)[0]
+    assert F > 0.9999
+    assert abs(F - 0.9999961847609591) < 1e-12
+    Fc = ro.calculate_fidelity_and_derivatives(cz_problem_closures(1000, T0), xs)[0]
+    assert abs(F - Fc) < 1e-13          # descriptor closures == literal RydbergTools builders
+    Fp = cpu_port.PortProblem(cz_problem(1000, T0)).fidelity_and_derivatives_batch(xs[:, None], 1)[0][0]
+    assert abs(F - Fp) < 1e-12          # C++ port (Pade-3/5 expm) == scipy expm
+
+
+def test_fidelity_gradient_validation():
+    """test/runtests.jl:292-354: analytic gradient vs forward FD with step eps, 5 trials."""
+    N = 50
+    fp = cz_problem(N, T0)
+    rng = np.random.default_rng(42)
+    for trial in range(5):
+        idx = rng.integers(0, N) if trial < 4 else N
+        xs = 2 * np.pi * rng.random(N + 1)
+        F0, g0, _, _ = ro.calculate_fidelity_and_derivatives(fp, xs)
+        xs[idx] += fp.unitary_problem.eps
+        F1 = ro.calculate_fidelity_and_derivatives(fp, xs)[0]
+        assert np.isclose((F1 - F0) / fp.unitary_problem.eps, g0[idx], rtol=1e-3, atol=1e-3)
+
+
+def test_error_sensitivity_gradient_validation():
+    """test/runtests.jl:48-113: F_d2err_dx vs forward FD (step 1e-4) of F_d2err."""
+    N = 200
+    fp = cz_problem(N, T0, ("amp",))
+    port = cpu_port.PortProblem(fp)
+    rng = np.random.default_rng(42)
+    for trial in range(2):
+        idx = N if trial == 1 else rng.integers(0, N)
+        xs = 2 * np.pi * rng.random(N + 1)
+        _, _, s0, s0dx = port.fidelity_and_derivatives_batch(xs[:, None], 1)
+        xs[idx] += 1e-4
+        _, _, s1, _ = port.fidelity_and_derivatives_batch(xs[:, None], 1)
+        assert np.isclose((s1[0, 0] - s0[0, 0]) / 1e-4, s0dx[idx, 0, 0], rtol=1e-3, atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def optimised_pulse():
+    """test/runtests.jl:167-226 / 356-416: 40 L-BFGS iterations from a small random pulse."""
+    N = 200
+    fp = cz_problem(N, T0)
+    port = cpu_port.PortProblem(fp)
+    rng = np.random.default_rng(42)
+    x0 = np.concatenate([2 * np.pi * 0.001 * rng.random(N), [2 * np.pi * rng.random()]])
+    from scipy.optimize import minimize
+
+    def fg(x):
+        c, g = port.cost_and_grad_batch(x[:, None], (), 1)
+        c, g = float(c[0]), g[:, 0].copy()
+        r1, j1, r2, j2 = ro.runtests_regularization_cost_phase(x[:N])
+        g[:N] += 1e-6 * j1 + 1e-6 * j2
+        return c + 1e-6 * r1 + 1e-6 * r2, g
+
+    res = minimize(fg, x0, jac=True, method="L-BFGS-B", options={"maxiter": 200, "ftol": 1e-15, "gtol": 3e-10})
+    return fp, res.x
+
+
+def test_gradient_based_pulse_optimisation(optimised_pulse):
+    """test/runtests.jl:356-416: optimised infidelity < 1e-6 (scipy L-BFGS-B stands in for Optim.LBFGS)."""
+    fp, x = optimised_pulse
+    F = ro.calculate_fidelity_and_derivatives(fp, x)[0]
+    assert 1 - F < 1e-6
+
+
+def test_error_sensitivity_vs_second_difference(optimised_pulse):
+    """test/runtests.jl:228-289: F_d2err vs central second difference of F over H0(+-eps2)."""
+    fp, x = optimised_pulse
+    e2 = fp.unitary_problem.eps2
+    F0 = ro.calculate_fidelity_and_derivatives(fp, x)[0]
+    Fp = ro.calculate_fidelity_and_derivatives(cz_problem(200, T0, eps=e2), x)[0]
+    Fm = ro.calculate_fidelity_and_derivatives(cz_problem(200, T0, eps=-e2), x)[0]
+    F1_d2 = ro.calculate_fidelity_and_derivatives(cz_problem(200, T0, ("amp",)), x)[2]
+    assert np.isclose((Fp + Fm - 2 * F0) / e2 ** 2, F1_d2[0], rtol=1e-3, atol=1e-2)
+
+
+def test_reduced_vs_full_hamiltonian(optimised_pulse):
+    """test/runtests.jl:418-529: 5-level symmetric vs 7-level full-blockaded sensitivities agree."""
+    _, x = optimised_pulse
+    s5 = cpu_port.PortProblem(cz_problem(200, T0, ("amp", "freq"))).fidelity_and_derivatives_batch(x[:, None], 1)[2][:, 0]
+    s7 = cpu_port.PortProblem(cz_problem(200, T0, ("amp", "freq"), model="full_blockaded")).fidelity_and_derivatives_batch(x[:, None], 1)[2][:, 0]
+    assert np.allclose(s5, s7, rtol=1e-3, atol=1e-3)
+
+
+def test_fidelity_response_vs_sensitivity(optimised_pulse):
+    """test/runtests.jl:531-619 and examples/time_optimal_cz.jl:82-84: -F_d2err == 2 R(omega=0), direct and FFT."""
+    _, x = optimised_pulse
+    fp = cz_problem(200, T0, ("amp", "freq"))
+    s = ro.calculate_fidelity_and_derivatives(fp, x)[2]
+    R = ro.calculate_fidelity_response(fp, x, np.linspace(0, 3, 5))
+    Rf, fr = ro.calculate_fidelity_response_fft(fp, x, oversampling=2)
+    assert np.allclose(-s, 2 * R[0], rtol=1e-3, atol=1e-3)
+    assert np.allclose(-s, 2 * Rf[0], rtol=1e-3, atol=1e-3)
+    assert fr[0] == 0 and len(fr) == 400
+
+
+def test_fp64_restatement_vs_exact_semantics_noise_floor():
+    """The FP64 restatement differs from the exact value of the same formulas only by the rounding
+    noise the finite-difference quotients amplify: F at 1e-13, derivatives at <= 1e-5
+    of their largest component.  This is the floor any FP64 implementation of the reference shares."""
+    fp = cz_problem(12, 7.613 * 12 / 100, ("amp",))
+    x = 2 * np.pi * np.random.default_rng(5).random(13)
+    a = ro.calculate_fidelity_and_derivatives(fp, x)
+    e = eo.calculate_fidelity_and_derivatives(fp, x)
+    assert abs(a[0] - e[0]) < 1e-13
+    for u, v in zip(a[1:], e[1:]):
+        assert np.abs(np.asarray(u) - v).max() <= 1e-5 * np.abs(v).max()
+
+
+def test_golden_fixtures_match_oracles():
+    """Committed fixtures are reproduced by the FP64 oracle (bitwise inputs, values within noise)."""
+    from pathlib import Path
+    from cases import golden_cases
+    gdir = Path(__file__).parent / "golden"
+    for name, (fp, x) in golden_cases().items():
+        z = np.load(gdir / f"{name}.npz")
+        assert np.array_equal(z["x"], x)
+        a = ro.calculate_fidelity_and_derivatives(fp, x)
+        assert abs(a[0] - float(z["exact_F"])) < 1e-13
+        for k, v in zip(["F_dx", "F_d2err", "F_d2err_dx"], a[1:]):
+            if z["exact_" + k].size:
+                assert np.abs(np.asarray(v) - z["exact_" + k]).max() <= 1e-5 * np.abs(z["exact_" + k]).max()
+                assert np.allclose(np.asarray(v), z["fp64_" + k], rtol=0, atol=1e-7 * max(1e-3, np.abs(z["fp64_" + k]).max()))
+
+
+def test_cpp_port_matches_numpy_oracle():
+    from cases import detuned_problem, random_pulse
+    for fp, p in [(cz_problem(30, 3.0, ("amp", "freq")), 1), (detuned_problem(11, 1.3, ("amp", "freq")), 2),
+                  (cz_problem(9, 1.0, ("freq",), model="full_blockaded"), 1)]:
+        x = random_pulse(fp, p, 3)
+        a = ro.calculate_fidelity_and_derivatives(fp, x)
+        F, Fdx, F2, F2dx = cpu_port.PortProblem(fp, nparam=p).fidelity_and_derivatives_batch(x[:, None], 1)
+        assert abs(F[0] - a[0]) < 1e-12
+        assert np.abs(Fdx[:, 0] - a[1]).max() < 1e-5 * np.abs(a[1]).max()
+        assert np.abs(F2[:, 0] - a[2]).max() < 1e-5 * np.abs(a[2]).max()
+        assert np.abs(F2dx[:, :, 0] - a[3]).max() < 1e-5 * np.abs(a[3]).max()
+        c, g = cpu_port.PortProblem(fp, nparam=p).cost_and_grad_batch(x[:, None], [1e-4, 2e-4], 1)
+        b = ro.cost_and_gradient(fp, x, [1e-4, 2e-4][:len(fp.unitary_problem.error_sources)])
