@@ -198,7 +198,10 @@ def main():
     coeff = [1e-4] * args.nerr
 
     ctx = Context(local)
-    stream = torch.cuda.current_stream()
+    # All work (library kernels, NCCL, timing events) goes on one non-default torch stream.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     prob = Problem(make_problem(N, args.nerr), ctx)
 

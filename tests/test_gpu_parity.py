@@ -4,9 +4,12 @@ Tolerances (stated per check):
   * vs the exact-semantics golden fixtures (mpmath, tests/golden/): 1e-10 relative to the largest
     component of each output -- the north-star tolerance.  The CUDA path forms differenced
     exponentials, so it sits ~1e-15 from the exact value of the reference's finite-difference formulas.
-  * vs the FP64 literal restatement (numpy / C++ port): F at 1e-12; derivative outputs at 2e-5 of the
-    largest component, which is the restatement's own finite-difference noise floor (measured in
-    tests/test_oracle_structure.py::test_fp64_restatement_vs_exact_semantics_noise_floor).
+  * vs the FP64 literal restatement (numpy / C++ port): F at 1e-12; eps-quotient outputs (F_dx, F_d2err)
+    at 2e-5 and the eps2^2-quotient output (F_d2err_dx) at 2e-4 of the largest component.  These are the
+    restatement's own finite-difference noise floors (1e-16 rounding amplified by 1/eps = 1e8 resp.
+    1/eps2^2 = 1e8 and accumulated over ntimes; measured in
+    tests/test_oracle_structure.py::test_fp64_restatement_vs_exact_semantics_noise_floor), not a
+    property of the CUDA path, which the golden test pins at 1e-10.
 """
 import os
 from pathlib import Path
@@ -65,12 +68,12 @@ def test_batch_vs_fp64_restatement(gpu_ctx, N, errors, model, B):
     assert np.abs(F - pF).max() < 1e-12
     assert relmax(Fdx, pFdx) < 2e-5
     assert relmax(F2, pF2) < 2e-5
-    assert relmax(F2dx, pF2dx) < 2e-5
+    assert relmax(F2dx, pF2dx) < 2e-4
     coeff = [1e-4, 3e-4][:len(errors)]
     c, g = rg.cost_and_gradient_batch(fp, X, coeff)
     pc, pg = cpu_port.PortProblem(fp).cost_and_grad_batch(X, coeff)
     assert np.abs(c - pc).max() < 1e-9
-    assert relmax(g, pg) < 2e-5
+    assert relmax(g, pg) < 2e-4
     # cost/grad epilogue is exactly the reference's combination of the four outputs (src/FidelityCalculations.jl:178-184)
     c2 = 1 - F + sum(coeff[e] * F2[e] ** 2 for e in range(len(errors)))
     g2 = -Fdx + sum(2 * coeff[e] * F2[e][None, :] * F2dx[:, e, :] for e in range(len(errors)))
@@ -87,7 +90,7 @@ def test_additional_parameter_dependent_hamiltonian(gpu_ctx):
         assert abs(F[b] - a[0]) < 1e-12
         assert relmax(Fdx[:, b], a[1]) < 2e-5
         assert relmax(F2[:, b], a[2]) < 2e-5
-        assert relmax(F2dx[:, :, b], a[3]) < 2e-5
+        assert relmax(F2dx[:, :, b], a[3]) < 2e-4
 
 
 def test_chunk_length_independence(gpu_ctx, monkeypatch):
