@@ -126,7 +126,7 @@ class Context:
     def launch_count(self):
         return int(self.lib.rg_ctx_launch_count(self.handle))
 
-    KERNELS = ("k_steps", "k_steps_so", "k_scan", "k_grad", "k_grad_err", "epilogue", "analysis")
+    KERNELS = ("k_steps", "k_steps_so", "k_scan", "k_grad", "k_grad_err", "epilogue", "analysis", "k_chunk_agg")
 
     def set_timing(self, enable):
         self.check(self.lib.rg_ctx_set_timing(self.handle, 1 if enable else 0))

@@ -8,8 +8,9 @@
 #include <string>
 #include <vector>
 
-enum { RG_K_STEPS = 0, RG_K_STEPS_SO = 1, RG_K_SCAN = 2, RG_K_GRAD = 3, RG_K_GRAD_ERR = 4, RG_K_EPILOGUE = 5, RG_K_ANALYSIS = 6, RG_NKERNELS = 8 };
+enum { RG_K_STEPS = 0, RG_K_STEPS_SO = 1, RG_K_SCAN = 2, RG_K_GRAD = 3, RG_K_GRAD_ERR = 4, RG_K_EPILOGUE = 5, RG_K_ANALYSIS = 6, RG_K_AGG = 7, RG_NKERNELS = 8 };
 #include "rg_smalld.cuh"
+#include "rg_steps_t.cuh"
 #include "rg_analysis.cuh"
 #include "rg_peak.cuh"
 
@@ -63,6 +64,12 @@ struct rg_problem {
     std::vector<void*> owned;          // device allocations of the descriptor
     int any_add_dep = 0;
     int chunk_override = 0;
+    int force_dense = 0;      // RG_DENSE=1: treat H as dense (no structural-zero skipping)
+    int force_group = 0;      // RG_GROUP=1: force the group-per-chunk k_steps kernel
+    TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
+    int tri_ok = 0;
+    double tri_density = 1.0;
+    unsigned tri_union = 0;   // union of all structural masks
     // workspaces
     DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2;
     int has_target = 0;
@@ -316,6 +323,50 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (desc->table && desc->ntable_cols > 0) tab.assign(desc->table, desc->table + (size_t)desc->ntable_cols * P.N);
     P.table = upload(pr, tab);
     if (const char* s = getenv("RG_CHUNK")) pr->chunk_override = atoi(s);
+    if (const char* s = getenv("RG_DENSE")) pr->force_dense = atoi(s);
+    if (const char* s = getenv("RG_GROUP")) pr->force_group = atoi(s);
+    // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
+    if (P.hermitian && d <= 5 && P.nterms <= RG_T_MAX_TERMS) {
+        const int npos = d * (d + 1) / 2;
+        std::vector<std::vector<std::pair<int, std::pair<double, double>>>> lists(npos);
+        std::vector<double> colw((size_t)std::max(1, P.nterms) * d, 0.0);
+        std::vector<int> used(std::max(1, P.nterms), 0);
+        TriPlanDev& tp = pr->tri;
+        tp.maskA = 0;
+        for (int v = 0; v < RG_MAX_VARS; ++v) tp.maskVar[v] = 0;
+        for (int e = 0; e < RG_MAX_ERR; ++e) tp.maskErr[e] = 0;
+        for (auto& en : he) {
+            colw[(size_t)en.term * d + en.col] += std::sqrt(en.vr * en.vr + en.vi * en.vi);
+            if (en.row > en.col) continue;
+            const int pos = en.col * (en.col + 1) / 2 + en.row;
+            lists[pos].push_back({en.term, {en.vr, en.vi}});
+            used[en.term] = 1;
+            const DevTerm& t = ht[en.term];
+            if (t.owner == RG_OWNER_H0) {
+                tp.maskA |= 1u << pos;
+                for (int v = 0; v < P.nvar; ++v)
+                    for (int f = 0; f < t.nf; ++f)
+                        if (t.f[f].kind <= RG_F_EXPI && t.f[f].space == P.var_space[v] && t.f[f].index == P.var_index[v]) tp.maskVar[v] |= 1u << pos;
+            } else {
+                tp.maskErr[t.owner] |= 1u << pos;
+            }
+        }
+        std::vector<int> ptr(npos + 1, 0), term;
+        std::vector<double> val;
+        for (int pos = 0; pos < npos; ++pos) {
+            for (auto& x : lists[pos]) { term.push_back(x.first); val.push_back(x.second.first); val.push_back(x.second.second); }
+            ptr[pos + 1] = (int)term.size();
+        }
+        tp.nent = (int)term.size();
+        tp.ptr = upload(pr, ptr); tp.term = upload(pr, term); tp.val = upload(pr, val);
+        tp.colw = upload(pr, colw); tp.used = upload(pr, used);
+        unsigned all = tp.maskA;
+        for (int v = 0; v < P.nvar; ++v) all |= tp.maskVar[v];
+        for (int e = 0; e < P.e; ++e) all |= tp.maskErr[e];
+        pr->tri_density = (double)__builtin_popcount(all) / npos;
+        pr->tri_union = all;
+        pr->tri_ok = 1;
+    }
     if (cudaGetLastError() != cudaSuccess || !P.terms || !P.table) return fail(RG_ERR_CUDA, "descriptor upload failed");
     *out = pr;
     return RG_OK;
@@ -396,26 +447,59 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         iFdx = pr->Fdx.as<double>();
     }
 
-    // ---- K1: step propagators + first-order differences + chunk aggregates
-    {
-        const int gs = k1_group_stride(D, P.nterms, ne);
+    // ---- K1: step propagators + first-order differences (+ chunk aggregates)
+    constexpr bool kThreadOK = (D <= 5);
+    if (kThreadOK && pr->tri_ok && !pr->force_group) {
+        // Hermitian fast path: one thread per time step, triangles in registers; aggregates in a second kernel.
+        constexpr int DT = kThreadOK ? D : 2;
+        constexpr unsigned FULL = (1u << (DT * (DT + 1) / 2)) - 1u;
+        // Compile-time structural masks instantiated ahead of time (upper-triangle bit = k(k+1)/2 + i):
+        //   5-level symmetric-blockaded Rydberg model (src/RydbergTools.jl:31-39): drive (1,3),(2,4); detuning (3,3),(4,4).
+        constexpr unsigned M5_DRIVE = (1u << 7) | (1u << 12), M5_FULL = M5_DRIVE | (1u << 9) | (1u << 14);
+        const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
+        const long long items = (long long)B * P.N;
+        const int grid = (int)((items + 127) / 128);
+        const unsigned need = pr->force_dense ? FULL : pr->tri_union;
+        {
+            KTimer kt(ctx, RG_K_STEPS);
+            if (DT == 5 && (need & ~M5_DRIVE) == 0)
+                k_steps_t<DT, (DT == 5 ? M5_DRIVE : FULL)><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+            else if (DT == 5 && (need & ~M5_FULL) == 0)
+                k_steps_t<DT, (DT == 5 ? M5_FULL : FULL)><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+            else
+                k_steps_t<DT, FULL><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+        }
+        const int gs = kagg_group_stride(D, ne);
         int wpc = 4;
         while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
-        const size_t smem = (size_t)wpc * G * gs * cb;
-        int rc = set_smem(ctx, k_steps<D>, smem);
+        const size_t smem2 = (size_t)wpc * G * gs * cb;
+        int rc = set_smem(ctx, k_chunk_agg<D>, smem2);
+        if (rc) return rc;
+        const long long citems = (long long)B * nc;
+        const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_AGG);
+        k_chunk_agg<D><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+    } else {
+        const int gs = k1_group_stride(D, P.nterms, ne);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps<D, false>, smem);
         if (rc) return rc;
         const long long items = (long long)B * nc;
         const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
         KTimer kt(ctx, RG_K_STEPS);
-        k_steps<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
-                                                pr->Wlb.as<cplx>(), ctx->d_status);
+        k_steps<D, false><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+                                                       pr->Wlb.as<cplx>(), ctx->d_status);
     }
     // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
     if (ne > 0 && want_grad && P.nvar > 0) {
         const int gs = k1b_group_stride(D, P.nterms);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
         int wpc = 4;
-        while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
-        const size_t smem = (size_t)wpc * G * gs * cb;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
         int rc = set_smem(ctx, k_steps_so<D>, smem);
         if (rc) return rc;
         const long long items = (long long)B * P.N;

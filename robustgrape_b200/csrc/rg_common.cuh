@@ -87,10 +87,19 @@ __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int psp
     if (f.kind == RG_F_VAR) { val = cmk(u, 0.0); del = cmk(hu, 0.0); return; }
     double s, co;
     sincos(u, &s, &co);
-    double sh = 0.0, s2 = 0.0;      // sin(hu), sin(hu/2)
-    if (dep) { sh = sin(hu); s2 = sin(0.5 * hu); }
     // e^{ihu} - 1 = -2 sin^2(hu/2) + i sin(hu)
-    const double er = -2.0 * s2 * s2, ei = sh;
+    double er = 0.0, ei = 0.0;
+    if (dep) {
+        if (fabs(hu) < 1e-3) {
+            // series: truncation < hu^6/5040 relative, i.e. < 2e-22 -- below double rounding
+            const double h2 = hu * hu;
+            ei = hu * (1.0 - h2 * (1.0 / 6.0) * (1.0 - h2 * (1.0 / 20.0)));
+            er = -0.5 * h2 * (1.0 - h2 * (1.0 / 12.0) * (1.0 - h2 * (1.0 / 30.0)));
+        } else {
+            const double s2 = sin(0.5 * hu);
+            ei = sin(hu); er = -2.0 * s2 * s2;
+        }
+    }
     if (f.kind == RG_F_EXPI) {
         val = cmk(co, s);
         del = cmk(co * er - s * ei, co * ei + s * er);

@@ -33,6 +33,7 @@ __host__ __device__ inline int k1_group_stride(int D, int nterms, int ne) {
     return rg_odd((4 + ne) * D * D + 2 * nterms);
 }
 __host__ __device__ inline int k1b_group_stride(int D, int nterms) { return rg_odd(4 * D * D + 4 * nterms); }
+__host__ __device__ inline int kagg_group_stride(int D, int ne) { return rg_odd((2 * (1 + ne) + ne) * D * D + 1); }
 __host__ __device__ inline int k2_group_stride(int D) { return rg_odd(14 * D * D + D + 1); }
 __host__ __device__ inline int k3_group_stride(int D, int nload) { return rg_odd(2 * nload * D * D + D + 1); }
 
@@ -41,6 +42,30 @@ template <int D> struct GroupInfo {
     static constexpr unsigned amask = (G * D == 32) ? 0xffffffffu : ((1u << (G * D)) - 1u);
 };
 
+
+// ------------------------------------------------------------------ descriptor staging
+// The term list, entry list and column pointers are copied to shared memory once per CTA so the
+// per-step prologue never waits on global memory for them.
+struct StagedDesc { const DevTerm* terms; const DevEntry* ents; const int* colptr; };
+__host__ __device__ inline size_t rg_align16(size_t n) { return (n + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t staged_desc_bytes(int nterms, int nent, int d) {
+    return rg_align16((size_t)nterms * sizeof(DevTerm)) + rg_align16((size_t)nent * sizeof(DevEntry)) + rg_align16((size_t)(d + 1) * sizeof(int));
+}
+// must be called by every thread of the CTA (contains __syncthreads)
+__device__ inline StagedDesc stage_desc(const DevProblem& P, unsigned char* sm) {
+    StagedDesc sd;
+    DevTerm* t = reinterpret_cast<DevTerm*>(sm);
+    DevEntry* e = reinterpret_cast<DevEntry*>(sm + rg_align16((size_t)P.nterms * sizeof(DevTerm)));
+    int* cp = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(e) + rg_align16((size_t)P.nent * sizeof(DevEntry)));
+    const int nt4 = P.nterms * (int)(sizeof(DevTerm) / 4), ne4 = P.nent * (int)(sizeof(DevEntry) / 4);
+    for (int i = threadIdx.x; i < nt4; i += blockDim.x) reinterpret_cast<int*>(t)[i] = reinterpret_cast<const int*>(P.terms)[i];
+    for (int i = threadIdx.x; i < ne4; i += blockDim.x) reinterpret_cast<int*>(e)[i] = reinterpret_cast<const int*>(P.ents)[i];
+    for (int i = threadIdx.x; i <= P.d; i += blockDim.x) cp[i] = P.colptr[i];
+    __syncthreads();
+    sd.terms = t; sd.ents = e; sd.colptr = cp;
+    return sd;
+}
+
 // ------------------------------------------------------------------ coefficient variants
 // Fill coef[t] for all terms (distributed over the group's lanes) for one matrix variant.
 //   VK_BASE   : H0 terms, value                         (scaled by -i dt)
@@ -48,12 +73,12 @@ template <int D> struct GroupInfo {
 //   VK_ERR    : error-source `es` terms at err=errv      (scaled by -i dt)
 //   VK_ERR_DX : error-source `es` terms at err=errv, difference in variable v
 template <int D>
-__device__ inline void fill_coefs(const DevProblem& P, cplx* coef, int kind, int es, double errv,
+__device__ inline void fill_coefs(const DevProblem& P, const DevTerm* terms, cplx* coef, int kind, int es, double errv,
                                   int pspace, int pindex, double h, const double* xk, const double* xadd,
                                   int k, int l) {
     EvalCtx ec{xk, xadd, errv, P.table, P.N, k};
     for (int t = l; t < P.nterms; t += D) {
-        const DevTerm& tm = P.terms[t];
+        const DevTerm& tm = terms[t];
         cplx out = cmk(0.0, 0.0);
         const bool isH0 = (tm.owner == RG_OWNER_H0);
         const bool use = (kind == VK_BASE || kind == VK_DX) ? isH0 : (tm.owner == es);
@@ -202,6 +227,95 @@ __device__ __forceinline__ void horner_so(const cplx* mA, const cplx* mAl, const
     }
 }
 
+
+// ------------------------------------------------------------------ skew-Hermitian fast path
+// For Hermitian H (and Hermitian perturbations) A = -i dt H and dA are skew-Hermitian:
+// M[k][i] = -conj(M[i][k]).  Only the upper triangle is loaded, once per pass, into registers, so the
+// Horner loop runs without any shared-memory traffic (the dense loop above is LSU-wavefront bound:
+// every 16-byte operand costs 4 wavefronts and feeds only 4-8 DFMA).
+template <int D> struct Tri {
+    static constexpr int n = D * (D + 1) / 2;
+    __host__ __device__ static constexpr int idx(int i, int k) { return k * (k + 1) / 2 + i; }   // i <= k
+};
+template <int D>
+__device__ __forceinline__ void load_tri(const cplx* M, cplx (&t)[Tri<D>::n]) {
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i <= k; ++i) t[Tri<D>::idx(i, k)] = M[i + D * k];
+}
+// acc -= conj(a) * b
+__device__ __forceinline__ void cfma_nconj(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+template <int D>
+__device__ __forceinline__ void horner_fo_tri(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], int l, int m,
+                                              cplx (&y)[D], cplx (&dl)[D]) {
+    // first iteration: Y = I + A/m, Dl = dA/m  -> column l of the (skew-Hermitian) matrices
+    {
+        const double inv = c_inv_j[m];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { y[i] = cmk(0.0, 0.0); dl[i] = cmk(0.0, 0.0); }
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const cplx a = ta[Tri<D>::idx(i, k)], d = td[Tri<D>::idx(i, k)];
+                if (k == l) { y[i] = cscale(a, inv); dl[i] = cscale(d, inv); }
+                if (i == l && i != k) { y[k] = cscale(cmk(-a.x, a.y), inv); dl[k] = cscale(cmk(-d.x, d.y), inv); }
+            }
+#pragma unroll
+        for (int i = 0; i < D; ++i) if (i == l) y[i].x += 1.0;
+    }
+    for (int j = m - 1; j >= 1; --j) {
+        const double inv = c_inv_j[j];
+        cplx t[D], u[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { t[i] = cmk(0.0, 0.0); u[i] = cmk(0.0, 0.0); }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const cplx a = ta[Tri<D>::idx(i, k)], d = td[Tri<D>::idx(i, k)];
+                const cplx sk = cadd(y[k], dl[k]);
+                cfma(t[i], a, y[k]);
+                cfma(u[i], a, dl[k]);
+                cfma(u[i], d, sk);
+                if (i != k) {
+                    const cplx si = cadd(y[i], dl[i]);
+                    cfma_nconj(t[k], a, y[i]);
+                    cfma_nconj(u[k], a, dl[i]);
+                    cfma_nconj(u[k], d, si);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            y[i] = cscale(t[i], inv);
+            if (i == l) y[i].x += 1.0;
+            dl[i] = cscale(u[i], inv);
+        }
+    }
+}
+
+// Fused pass over a unitary step matrix U (shared memory): cp = U^dagger c and gn = g U.
+// Each loaded element feeds two complex FMAs (the two separate passes were LSU-wavefront bound).
+template <int D>
+__device__ __forceinline__ void rewind_advance(const cplx* __restrict__ M, const cplx (&c)[D], const cplx (&g)[D],
+                                               cplx (&cp)[D], cplx (&gn)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) { cp[j] = cmk(0.0, 0.0); gn[j] = cmk(0.0, 0.0); }
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const cplx u = M[i + D * j];
+            cfma_conj(cp[j], u, c[i]);
+            cfma(gn[j], g[i], u);
+        }
+}
+
 // out = M * v   (M in shared memory, column-major)
 template <int D>
 __device__ __forceinline__ void matvec(const cplx* __restrict__ M, const cplx (&v)[D], cplx (&out)[D]) {
@@ -269,14 +383,16 @@ __device__ __forceinline__ double redot(const cplx (&g)[D], const cplx (&t)[D]) 
 // Work item = (pulse, chunk of L steps).  Per step: A, then one Horner pass per first-order object
 // (variables, then error sources).  The chunk product q and the error aggregates wl live in shared
 // memory (private columns) so the Horner loops own the register file.
-template <int D>
-__global__ void __launch_bounds__(128)
+template <int D, bool TRI>
+__global__ void __launch_bounds__(128, TRI ? 2 : 1)
 k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
         cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb, int* __restrict__ status) {
     constexpr int G = GroupInfo<D>::G;
     constexpr unsigned amask = GroupInfo<D>::amask;
     constexpr int DD = D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ cplx smem[];
+    const StagedDesc sd = stage_desc(P, reinterpret_cast<unsigned char*>(smem));
     if (lane >= G * D) return;
     const int g = lane / D, l = lane - g * D;
     const long long total = (long long)B * nc;
@@ -285,9 +401,8 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
     if (!live) item = total - 1;
     const int b = (int)(item / nc), ch = (int)(item % nc);
 
-    extern __shared__ cplx smem[];
     const int nt = P.nterms, ne = P.e, nv = P.nvar;
-    cplx* base = smem + (size_t)(warp * G + g) * k1_group_stride(D, nt, ne);
+    cplx* base = smem + staged_desc_bytes(P.nterms, P.nent, D) / sizeof(cplx) + (size_t)(warp * G + g) * k1_group_stride(D, nt, ne);
     cplx* mA = base;
     cplx* mD = base + DD;
     cplx* mX = base + 2 * DD;
@@ -309,24 +424,34 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
     const int nfo = nv + ne;
     // Uniform trip count across the warp (groups sync with __syncwarp): steps past the end of the
     // pulse are ghost steps with A = 0, i.e. U = I exactly and all differences 0; nothing is stored.
+    double xnext[RG_MAX_MAIN];
+    for (int i = 0; i < P.p; ++i) xnext[i] = xp[(size_t)k0 * P.p + i];
     for (int kk = 0; kk < L; ++kk) {
         const bool ghost = (k0 + kk >= k1);
         const int k = ghost ? (k1 - 1) : (k0 + kk);
         const bool st = live && !ghost;
         double xk[RG_MAX_MAIN];
-        for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        {   // controls of this step were fetched one iteration ago; fetch the next step's now
+            const int kn = min(k0 + kk + 1, k1 - 1);
+            for (int i = 0; i < P.p; ++i) { xk[i] = xnext[i]; xnext[i] = xp[(size_t)kn * P.p + i]; }
+        }
         cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
 
         // ---- base matrix A = -i dt H0(x_k)
-        fill_coefs<D>(P, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
+        fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
         __syncwarp(amask);
-        assemble_col<D>(P.ents, P.colptr, coef, mA, l, ghost);
+        assemble_col<D>(sd.ents, sd.colptr, coef, mA, l, ghost);
         double nrm = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
         int m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
         m = __reduce_max_sync(amask, m);
         if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }
+        cplx ta[TRI ? Tri<D>::n : 1];
+        if (TRI) {
+            __syncwarp(amask);
+            load_tri<D>(mA, reinterpret_cast<cplx(&)[Tri<D>::n]>(ta));
+        }
 
         // ---- first-order objects: variables then error sources (at least one pass, for U itself)
         for (int o = 0; o < max(nfo, 1); ++o) {
@@ -337,15 +462,21 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
                 const int sp = P.var_space[o], ix = P.var_index[o];
                 const double v = (sp == RG_S_MAIN) ? xk[ix] : xadd[ix];
                 const double h = __dsub_rn(__dadd_rn(v, P.eps), v);     // the step actually taken
-                fill_coefs<D>(P, cf, VK_DX, 0, 0.0, sp, ix, h, xk, xadd, k, l);
+                fill_coefs<D>(P, sd.terms, cf, VK_DX, 0, 0.0, sp, ix, h, xk, xadd, k, l);
             } else {
-                fill_coefs<D>(P, cf, VK_ERR, o - nv, P.eps, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
+                fill_coefs<D>(P, sd.terms, cf, VK_ERR, o - nv, P.eps, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
             }
             __syncwarp(amask);
-            assemble_col<D>(P.ents, P.colptr, cf, mD, l, ghost);
+            assemble_col<D>(sd.ents, sd.colptr, cf, mD, l, ghost);
             __syncwarp(amask);
             cplx y[D], dl[D];
-            horner_fo<D>(mA, mD, l, m, y, dl);
+            if (TRI) {
+                cplx td[TRI ? Tri<D>::n : 1];
+                load_tri<D>(mD, reinterpret_cast<cplx(&)[Tri<D>::n]>(td));
+                horner_fo_tri<D>(reinterpret_cast<cplx(&)[Tri<D>::n]>(ta), reinterpret_cast<cplx(&)[Tri<D>::n]>(td), l, m, y, dl);
+            } else {
+                horner_fo<D>(mA, mD, l, m, y, dl);
+            }
             if (st && nfo > 0) {
                 cplx* dst = wsk + (size_t)(1 + o) * DD + l * D;
 #pragma unroll
@@ -428,6 +559,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     constexpr unsigned amask = GroupInfo<D>::amask;
     constexpr int DD = D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ cplx smem[];
+    const StagedDesc sd = stage_desc(P, reinterpret_cast<unsigned char*>(smem));
     if (lane >= G * D) return;
     const int g = lane / D, l = lane - g * D;
     const long long total = (long long)B * P.N;
@@ -436,9 +569,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     if (!live) item = total - 1;
     const int b = (int)(item / P.N), k = (int)(item % P.N);
 
-    extern __shared__ cplx smem[];
     const int nt = P.nterms, ne = P.e, nv = P.nvar;
-    cplx* base = smem + (size_t)(warp * G + g) * k1b_group_stride(D, nt);
+    cplx* base = smem + staged_desc_bytes(P.nterms, P.nent, D) / sizeof(cplx) + (size_t)(warp * G + g) * k1b_group_stride(D, nt);
     cplx* mA = base;
     cplx* mAl = base + DD;
     cplx* mBe = base + 2 * DD;
@@ -451,9 +583,9 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
     cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
 
-    fill_coefs<D>(P, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
+    fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
     __syncwarp(amask);
-    assemble_col<D>(P.ents, P.colptr, coef, mA, l);
+    assemble_col<D>(sd.ents, sd.colptr, coef, mA, l);
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
@@ -462,18 +594,18 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }
 
     for (int e = 0; e < ne; ++e) {
-        fill_coefs<D>(P, coef + 2 * nt, VK_ERR, e, P.eps2, RG_S_NONE, 0, 0.0, xk, xadd, k, l);   // beta
+        fill_coefs<D>(P, sd.terms, coef + 2 * nt, VK_ERR, e, P.eps2, RG_S_NONE, 0, 0.0, xk, xadd, k, l);   // beta
         __syncwarp(amask);
-        assemble_col<D>(P.ents, P.colptr, coef + 2 * nt, mBe, l);
+        assemble_col<D>(sd.ents, sd.colptr, coef + 2 * nt, mBe, l);
         for (int v = 0; v < nv; ++v) {
             const int sp = P.var_space[v], ix = P.var_index[v];
             const double val = (sp == RG_S_MAIN) ? xk[ix] : xadd[ix];
             const double h2 = __dsub_rn(__dadd_rn(val, P.eps2), val);
-            fill_coefs<D>(P, coef + nt, VK_DX, 0, 0.0, sp, ix, h2, xk, xadd, k, l);              // alpha
-            fill_coefs<D>(P, coef + 3 * nt, VK_ERR_DX, e, P.eps2, sp, ix, h2, xk, xadd, k, l);   // gamma
+            fill_coefs<D>(P, sd.terms, coef + nt, VK_DX, 0, 0.0, sp, ix, h2, xk, xadd, k, l);              // alpha
+            fill_coefs<D>(P, sd.terms, coef + 3 * nt, VK_ERR_DX, e, P.eps2, sp, ix, h2, xk, xadd, k, l);   // gamma
             __syncwarp(amask);
-            assemble_col<D>(P.ents, P.colptr, coef + nt, mAl, l);
-            assemble_col<D>(P.ents, P.colptr, coef + 3 * nt, mGa, l);
+            assemble_col<D>(sd.ents, sd.colptr, coef + nt, mAl, l);
+            assemble_col<D>(sd.ents, sd.colptr, coef + 3 * nt, mGa, l);
             __syncwarp(amask);
             cplx y[D], da[D], db[D], dab[D];
             horner_so<D>(mA, mAl, mBe, mGa, l, m, y, da, db, dab, amask);
@@ -841,8 +973,8 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         __syncwarp(amask);
         const cplx* mZ = cur;
         const cplx* mDe = cur + (nv + 1) * DD;
-        cplx cp[D];
-        matvec_adj<D>(mZ, c, cp);                       // c_{k-1} = U_k^dag c_k
+        cplx cp[D], gn[D];
+        rewind_advance<D>(mZ, c, gr, cp, gn);           // c_{k-1} = U_k^dag c_k  and  g_{k-1} = g_k U_k in one pass
         cplx wp[ERR ? D : 1];
         if (ERR) {
             cplx t[D];
@@ -901,8 +1033,6 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
 #pragma unroll
                 for (int i = 0; i < (ERR ? D : 1); ++i) { hr[i] = hn[i]; w[i] = wp[i]; }
             }
-            cplx gn[D];
-            vecmat<D>(gr, mZ, gn);
 #pragma unroll
             for (int i = 0; i < D; ++i) { gr[i] = gn[i]; c[i] = cp[i]; }
         }

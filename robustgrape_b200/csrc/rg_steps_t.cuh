@@ -1,0 +1,276 @@
+// rg_steps_t.cuh -- thread-per-time-step propagator kernel for Hermitian problems with d <= 5, and the
+// chunk-aggregate kernel that follows it.
+//
+// k_steps_t: one thread owns one (pulse, time step).  A = -i dt H and every perturbation matrix dA are
+//   skew-Hermitian, so their upper triangles (d(d+1)/2 complex numbers each) live in registers; the thread
+//   runs the (value, difference) Horner recurrence of rg_smalld.cuh column by column.  No shared-memory
+//   operand traffic, no warp synchronisation, all 32 lanes busy, and the coefficient evaluation (sincos)
+//   is done once per step instead of once per lane of a group.  Structural zeros of H (positions of the
+//   upper triangle no term touches) are skipped with warp-uniform branches when MASKED.
+// k_chunk_agg: per (pulse, chunk) group: Q_c = U_last ... U_first and Wl_c = dQ_c/derr from the stored
+//   step matrices (src/UnitaryCalculations.jl:46 restricted to a chunk).
+#pragma once
+#include "rg_smalld.cuh"
+
+#define RG_T_MAX_TERMS 16
+
+struct TriPlanDev {
+    int nent;                 // plan entries
+    const int* ptr;           // [npos+1] entry range of each upper-triangle position
+    const int* term;          // [nent] term index
+    const double* val;        // [nent*2] matrix value (re, im)
+    const double* colw;       // [nterms*d] column 1-norms of each term's matrix (for the ||A||_1 bound)
+    const int* used;          // [nterms] term has upper-triangle entries
+    unsigned maskA;           // positions touched by H0 terms
+    unsigned maskVar[RG_MAX_VARS];   // ... by H0 terms depending on variable v
+    unsigned maskErr[RG_MAX_ERR];    // ... by terms of error source e
+};
+
+struct StagedPlan { const int* ptr; const int* term; const cplx* val; const double* colw; const int* used; const DevTerm* terms; };
+__host__ __device__ inline size_t staged_plan_bytes(int nterms, int nent, int d) {
+    const int npos = d * (d + 1) / 2;
+    return rg_align16((size_t)nterms * sizeof(DevTerm)) + rg_align16((size_t)(npos + 1) * 4) + rg_align16((size_t)nent * 4) +
+           rg_align16((size_t)nent * 16) + rg_align16((size_t)nterms * d * 8) + rg_align16((size_t)nterms * 4);
+}
+__device__ inline StagedPlan stage_plan(const DevProblem& P, const TriPlanDev& tp, unsigned char* sm) {
+    const int npos = P.d * (P.d + 1) / 2;
+    unsigned char* p = sm;
+    int* t32 = reinterpret_cast<int*>(p); p += rg_align16((size_t)P.nterms * sizeof(DevTerm));
+    int* ptr = reinterpret_cast<int*>(p); p += rg_align16((size_t)(npos + 1) * 4);
+    int* term = reinterpret_cast<int*>(p); p += rg_align16((size_t)tp.nent * 4);
+    double* val = reinterpret_cast<double*>(p); p += rg_align16((size_t)tp.nent * 16);
+    double* colw = reinterpret_cast<double*>(p); p += rg_align16((size_t)P.nterms * P.d * 8);
+    int* used = reinterpret_cast<int*>(p);
+    const int nt4 = P.nterms * (int)(sizeof(DevTerm) / 4);
+    for (int i = threadIdx.x; i < nt4; i += blockDim.x) t32[i] = reinterpret_cast<const int*>(P.terms)[i];
+    for (int i = threadIdx.x; i <= npos; i += blockDim.x) ptr[i] = tp.ptr[i];
+    for (int i = threadIdx.x; i < tp.nent; i += blockDim.x) { term[i] = tp.term[i]; val[2 * i] = tp.val[2 * i]; val[2 * i + 1] = tp.val[2 * i + 1]; }
+    for (int i = threadIdx.x; i < P.nterms * P.d; i += blockDim.x) colw[i] = tp.colw[i];
+    for (int i = threadIdx.x; i < P.nterms; i += blockDim.x) used[i] = tp.used[i];
+    __syncthreads();
+    StagedPlan s{ptr, term, reinterpret_cast<const cplx*>(val), colw, used, reinterpret_cast<const DevTerm*>(t32)};
+    return s;
+}
+
+// (value, difference) Horner recurrence for one column l with register-resident triangles.
+// UMASK: compile-time superset of every position any matrix of this problem touches (pruned code and
+// registers for the rest); mA / mD: run-time (warp-uniform) masks of A and of the current dA, tested only
+// when UMASK is not the full triangle.
+template <int D, unsigned UMASK>
+__device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD,
+                                               int l, int m, cplx (&y)[D], cplx (&dl)[D]) {
+    constexpr bool MASKED = (UMASK != ((1u << Tri<D>::n) - 1u));
+    {
+        const double inv = c_inv_j[m];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { y[i] = cmk(0.0, 0.0); dl[i] = cmk(0.0, 0.0); }
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                if (!((UMASK >> Tri<D>::idx(i, k)) & 1u)) continue;
+                const cplx a = ta[Tri<D>::idx(i, k)], d = td[Tri<D>::idx(i, k)];
+                if (k == l) { y[i] = cscale(a, inv); dl[i] = cscale(d, inv); }
+                if (i == l && i != k) { y[k] = cscale(cmk(-a.x, a.y), inv); dl[k] = cscale(cmk(-d.x, d.y), inv); }
+            }
+#pragma unroll
+        for (int i = 0; i < D; ++i) if (i == l) y[i].x += 1.0;
+    }
+    for (int j = m - 1; j >= 1; --j) {
+        const double inv = c_inv_j[j];
+        cplx t[D], u[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { t[i] = cmk(0.0, 0.0); u[i] = cmk(0.0, 0.0); }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const int pos = Tri<D>::idx(i, k);
+                if (!((UMASK >> pos) & 1u)) continue;
+                if (!MASKED || ((mA >> pos) & 1u)) {
+                    const cplx a = ta[pos];
+                    cfma(t[i], a, y[k]);
+                    cfma(u[i], a, dl[k]);
+                    if (i != k) { cfma_nconj(t[k], a, y[i]); cfma_nconj(u[k], a, dl[i]); }
+                }
+                if (!MASKED || ((mD >> pos) & 1u)) {
+                    const cplx d = td[pos];
+                    cfma(u[i], d, cadd(y[k], dl[k]));
+                    if (i != k) cfma_nconj(u[k], d, cadd(y[i], dl[i]));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            y[i] = cscale(t[i], inv);
+            if (i == l) y[i].x += 1.0;
+            dl[i] = cscale(u[i], inv);
+        }
+    }
+}
+
+template <int D, unsigned UMASK>
+__global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 3)
+k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
+          int* __restrict__ status) {
+    constexpr int DD = D * D, NP = Tri<D>::n;
+    extern __shared__ cplx smem[];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    const long long total = (long long)B * P.N;
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = item < total;
+    if (!live) item = total - 1;
+    const int b = (int)(item / P.N), k = (int)(item % P.N);
+    const double* xp = X + (size_t)b * P.nx;
+    double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
+    for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
+    for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
+    const int nt = P.nterms, nv = P.nvar, ne = P.e, nfo = nv + ne;
+
+    cplx ca[RG_T_MAX_TERMS], cd[RG_T_MAX_TERMS];     // (-i dt) * coefficient, value and difference
+    cplx ta[NP], td[NP];
+    int m = 0;
+    for (int o = 0; o < max(nfo, 1); ++o) {
+        // ---- coefficients of this pass (and of A on the first pass)
+        int sp_ = RG_S_NONE, ix = 0, es = -3;
+        double h = 0.0, errv = 0.0;
+        if (nfo > 0 && o < nv) {
+            sp_ = P.var_space[o]; ix = P.var_index[o];
+            const double v = (sp_ == RG_S_MAIN) ? xk[ix] : xadd[ix];
+            h = __dsub_rn(__dadd_rn(v, P.eps), v);                 // the step actually taken (:50)
+        } else if (nfo > 0) { es = o - nv; errv = P.eps; }
+        EvalCtx ec{xk, xadd, errv, P.table, P.N, k};
+        for (int t = 0; t < nt; ++t) {
+            cplx base = cmk(0, 0), del = cmk(0, 0);
+            const DevTerm& tm = sp.terms[t];
+            const bool isH0 = tm.owner == RG_OWNER_H0;
+            if (sp.used[t] && (isH0 || tm.owner == es)) term_coef(tm, ec, sp_, ix, h, base, del);
+            if (o == 0) ca[t] = isH0 ? cmk(base.y * P.dt, -base.x * P.dt) : cmk(0, 0);
+            const cplx dsel = isH0 ? del : base;                   // error terms enter with their value at err = eps
+            cd[t] = (isH0 && es >= 0) ? cmk(0, 0) : cmk(dsel.y * P.dt, -dsel.x * P.dt);
+        }
+        // ---- triangles
+#pragma unroll
+        for (int pos = 0; pos < NP; ++pos) {
+            if (!((UMASK >> pos) & 1u)) continue;
+            cplx a = cmk(0, 0), d = cmk(0, 0);
+            for (int e = sp.ptr[pos]; e < sp.ptr[pos + 1]; ++e) {
+                const int t = sp.term[e];
+                const cplx v = sp.val[e];
+                if (o == 0) cfma(a, ca[t], v);
+                cfma(d, cd[t], v);
+            }
+            if (o == 0) ta[pos] = a;
+            td[pos] = d;
+        }
+        if (o == 0) {
+            // ||A||_1 <= max_k sum_t |c_t| * ||M_t[:,k]||_1
+            double nrm = 0.0;
+            for (int kk = 0; kk < D; ++kk) {
+                double s = 0.0;
+                for (int t = 0; t < nt; ++t) { const cplx c = ca[t]; s += sqrt(c.x * c.x + c.y * c.y) * sp.colw[t * D + kk]; }
+                nrm = fmax(nrm, s);
+            }
+            m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 1); m = 18; }
+        }
+        const unsigned mD = (nfo == 0) ? 0u : (o < nv ? tp.maskVar[o] : tp.maskErr[o - nv]);
+        // ---- columns
+        for (int l = 0; l < D; ++l) {
+            cplx y[D], dl[D];
+            horner_col_tri<D, UMASK>(ta, td, tp.maskA, mD, l, m, y, dl);
+            if (live) {
+                if (nfo > 0) {
+                    cplx* dst = wsk + (size_t)(1 + o) * DD + l * D;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dst[i] = dl[i];
+                }
+                if (o == 0) {
+                    cplx* dst = wsk + l * D;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dst[i] = y[i];
+                }
+            }
+        }
+    }
+}
+
+// Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
+template <int D>
+__global__ void __launch_bounds__(128)
+k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb) {
+    constexpr int G = GroupInfo<D>::G;
+    constexpr unsigned amask = GroupInfo<D>::amask;
+    constexpr int DD = D * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= G * D) return;
+    const int g = lane / D, l = lane - g * D;
+    const long long total = (long long)B * nc;
+    long long item = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * G + g;
+    const bool live = item < total;
+    if (!live) item = total - 1;
+    const int b = (int)(item / nc), ch = (int)(item % nc);
+    const int nv = P.nvar, ne = P.e;
+    const int nload = 1 + ne;
+
+    extern __shared__ cplx smem[];
+    cplx* base = smem + (size_t)(warp * G + g) * kagg_group_stride(D, ne);
+    cplx* buf0 = base;
+    cplx* buf1 = base + nload * DD;
+    cplx* wl = base + 2 * nload * DD + l * D;      // + e*DD, private columns
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * DD;
+    auto issue = [&](int k, cplx* dstbuf) {
+        const cplx* wsk = wsb + (size_t)k * P.nstore * DD;
+        for (int s = 0; s < nload; ++s) {
+            const int obj = (s == 0) ? 0 : (1 + nv + (s - 1));
+            const cplx* src = wsk + (size_t)obj * DD + l * D;
+            cplx* dst = dstbuf + s * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) cp_async16(dst + i, src + i);
+        }
+        cp_async_commit();
+    };
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    cplx q[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) q[i] = cmk(i == l ? 1.0 : 0.0, 0.0);
+    for (int e = 0; e < ne; ++e)
+#pragma unroll
+        for (int i = 0; i < D; ++i) wl[e * DD + i] = cmk(0.0, 0.0);
+    issue(k0, buf0);
+    for (int kk = 0; kk < L; ++kk) {
+        const bool ghost = (k0 + kk >= k1);
+        cplx* cur = (kk & 1) ? buf1 : buf0;
+        cplx* nxt = (kk & 1) ? buf0 : buf1;
+        if (kk + 1 < L) { issue(min(k0 + kk + 1, k1 - 1), nxt); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncwarp(amask);
+        if (!ghost) {
+            for (int e = 0; e < ne; ++e) {
+                cplx w[D], wn[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) w[i] = wl[e * DD + i];
+                matvec<D>(cur, w, wn);
+                matvec_acc<D>(cur + (1 + e) * DD, q, wn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) wl[e * DD + i] = wn[i];
+            }
+            cplx qn[D];
+            matvec<D>(cur, q, qn);
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[i] = qn[i];
+        }
+        __syncwarp(amask);
+    }
+    if (live) {
+        cplx* dst = Qb + ((size_t)b * nc + ch) * DD + l * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) dst[i] = q[i];
+        for (int e = 0; e < ne; ++e) {
+            cplx* dw = Wlb + (((size_t)b * nc + ch) * ne + e) * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) dw[i] = wl[e * DD + i];
+        }
+    }
+}
