@@ -409,14 +409,32 @@ static int set_smem(rg_ctx* ctx, K kern, size_t bytes) {
     return RG_OK;
 }
 
+// Structural patterns instantiated ahead of time (upper-triangle bit = k(k+1)/2 + i, i <= k).  A problem
+// whose union mask fits one of them gets kernels with the zero positions removed at compile time; anything
+// else runs the full (dense) instantiation.  (Arbitrary patterns: NVRTC specialisation, see DESIGN.md.)
+//   PAT_M5_DRIVE: 5-level symmetric-blockaded Rydberg model (src/RydbergTools.jl:31-39), drive only: (1,3),(2,4)
+//   PAT_M5_FULL : same plus the Rydberg detuning diagonal (3,3),(4,4) (frequency error / delta != 0)
+enum { PAT_FULL = 0, PAT_M5_DRIVE = 1, PAT_M5_FULL = 2 };
+template <int D, int PID> constexpr unsigned tri_mask_of() {
+    return (D == 5 && PID == PAT_M5_DRIVE) ? ((1u << 7) | (1u << 12))
+         : (D == 5 && PID == PAT_M5_FULL) ? ((1u << 7) | (1u << 12) | (1u << 9) | (1u << 14))
+         : ((D * (D + 1) / 2 >= 32) ? ~0u : ((1u << (D * (D + 1) / 2)) - 1u));
+}
+template <int D, int PID> constexpr u64 cmask_of() {
+    return (PID == PAT_FULL) ? full_cmask<D>() : closure_from_tri(D, tri_mask_of<D, PID>());
+}
+
 // Run the fused path for one slab of pulses already resident on the device.
 //   mode 0: fidelity + derivatives  -> dF, dFdx (+1 scale), dF2, dF2dx
 //   mode 1: cost + grad             -> dcost (in dF slot), dgrad (in dFdx slot)
-template <int D>
+template <int D, int PID>
 static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mode, const double* d_coeff,
                     double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
     rg_ctx* ctx = pr->ctx;
-    const DevProblem& P = pr->dp;
+    constexpr u64 CM = cmask_of<D, PID>();
+    constexpr int WSM = Pat<D, CM>::nnz;
+    DevProblem P = pr->dp;
+    P.wsm = WSM; P.cmask = CM;
     constexpr int G = GroupInfo<D>::G;
     const int DD = D * D, ne = P.e, nc = pl.nc, L = pl.L;
     cudaStream_t st = ctx->stream;
@@ -424,7 +442,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported by the fused path yet");
 
     const size_t cb = sizeof(cplx);
-    if (pr->ws.ensure((size_t)B * P.N * P.nstore * DD * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
+    if (pr->ws.ensure((size_t)B * P.N * P.nstore * WSM * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
         pr->Wlb.ensure(std::max<size_t>(16, (size_t)B * nc * ne * DD * cb)) || pr->Cb.ensure((size_t)B * nc * DD * cb) ||
         pr->Wb.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) || pr->Gb.ensure((size_t)B * nc * DD * cb) ||
         pr->G1b.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) ||
@@ -449,36 +467,29 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
 
     // ---- K1: step propagators + first-order differences (+ chunk aggregates)
     constexpr bool kThreadOK = (D <= 5);
-    if (kThreadOK && pr->tri_ok && !pr->force_group) {
+    const bool fast = kThreadOK && pr->tri_ok && !pr->force_group;
+    if (!fast && PID != PAT_FULL) RG_FAIL(ctx, RG_ERR_INVALID, "internal: structural pattern without the fast path");
+    if (fast) {
         // Hermitian fast path: one thread per time step, triangles in registers; aggregates in a second kernel.
         constexpr int DT = kThreadOK ? D : 2;
-        constexpr unsigned FULL = (1u << (DT * (DT + 1) / 2)) - 1u;
-        // Compile-time structural masks instantiated ahead of time (upper-triangle bit = k(k+1)/2 + i):
-        //   5-level symmetric-blockaded Rydberg model (src/RydbergTools.jl:31-39): drive (1,3),(2,4); detuning (3,3),(4,4).
-        constexpr unsigned M5_DRIVE = (1u << 7) | (1u << 12), M5_FULL = M5_DRIVE | (1u << 9) | (1u << 14);
+        constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
         const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
         const long long items = (long long)B * P.N;
         const int grid = (int)((items + 127) / 128);
-        const unsigned need = pr->force_dense ? FULL : pr->tri_union;
         {
             KTimer kt(ctx, RG_K_STEPS);
-            if (DT == 5 && (need & ~M5_DRIVE) == 0)
-                k_steps_t<DT, (DT == 5 ? M5_DRIVE : FULL)><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
-            else if (DT == 5 && (need & ~M5_FULL) == 0)
-                k_steps_t<DT, (DT == 5 ? M5_FULL : FULL)><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
-            else
-                k_steps_t<DT, FULL><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+            k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
         }
         const int gs = kagg_group_stride(D, ne);
         int wpc = 4;
         while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
         const size_t smem2 = (size_t)wpc * G * gs * cb;
-        int rc = set_smem(ctx, k_chunk_agg<D>, smem2);
+        int rc = set_smem(ctx, k_chunk_agg<D, CM>, smem2);
         if (rc) return rc;
         const long long citems = (long long)B * nc;
         const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
         KTimer kt(ctx, RG_K_AGG);
-        k_chunk_agg<D><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+        k_chunk_agg<D, CM><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
     } else {
         const int gs = k1_group_stride(D, P.nterms, ne);
         const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
@@ -532,11 +543,11 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
-            int rc = set_smem(ctx, k_grad<D, false>, smem);
+            int rc = set_smem(ctx, k_grad<D, false, CM>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), 1);
             KTimer kt(ctx, RG_K_GRAD);
-            k_grad<D, false><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+            k_grad<D, false, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
         }
@@ -545,11 +556,11 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
-            int rc = set_smem(ctx, k_grad<D, true>, smem);
+            int rc = set_smem(ctx, k_grad<D, true, CM>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), ne);
             KTimer kt(ctx, RG_K_GRAD_ERR);
-            k_grad<D, true><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+            k_grad<D, true, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 0.0, iF2dx, pr->addS.as<double>());
         }
@@ -578,8 +589,15 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
 
 static int dispatch_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mode, const double* d_coeff,
                          double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
+    const bool fast = pr->tri_ok && !pr->force_group && !pr->force_dense;
+    if (pr->dp.d == 5 && fast) {
+        if ((pr->tri_union & ~tri_mask_of<5, PAT_M5_DRIVE>()) == 0)
+            return run_slab<5, PAT_M5_DRIVE>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+        if ((pr->tri_union & ~tri_mask_of<5, PAT_M5_FULL>()) == 0)
+            return run_slab<5, PAT_M5_FULL>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+    }
     switch (pr->dp.d) {
-#define RG_CASE(D) case D: return run_slab<D>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+#define RG_CASE(D) case D: return run_slab<D, PAT_FULL>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
         RG_CASE(2) RG_CASE(3) RG_CASE(4) RG_CASE(5) RG_CASE(6) RG_CASE(7) RG_CASE(8) RG_CASE(9)
 #undef RG_CASE
     default: break;

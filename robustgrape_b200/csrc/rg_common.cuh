@@ -38,6 +38,8 @@ struct DevProblem {
     int hermitian;
     int nx;              // p*N + a
     int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
+    int wsm;             // complex elements stored per step matrix (d*d, or the closure pattern's nnz)
+    unsigned long long cmask;   // closure pattern of the stored matrices: bit (i + d*j)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -139,3 +141,38 @@ __device__ __forceinline__ int taylor_degree(double nrm) {
     if (nrm <= 1.10) return 18;
     return 99;   // needs scaling and squaring
 }
+
+// ---------------------------------------------------------------------------------------
+// Structural pattern of the step matrices.  If H only couples certain pairs of levels, U = exp(-i dt H)
+// and all its differences are confined to the reflexive-transitive closure of that coupling graph
+// (block-diagonal for the Rydberg models).  CM has bit (i + D*j) set for every element that can be
+// non-zero; only those are stored in the HBM workspace, loaded and multiplied.
+typedef unsigned long long u64;
+template <int D> __host__ __device__ constexpr u64 full_cmask() { return (D * D >= 64) ? ~0ull : ((1ull << (D * D)) - 1ull); }
+__host__ __device__ constexpr int cx_popc(u64 v) { int c = 0; while (v) { v &= v - 1; ++c; } return c; }
+// closure of an upper-triangle mask (bit k(k+1)/2 + i, i <= k) as a full d x d pattern
+__host__ __device__ constexpr u64 closure_from_tri(int d, unsigned tri) {
+    bool r[8][8] = {};
+    for (int i = 0; i < d; ++i) r[i][i] = true;
+    for (int k = 0; k < d; ++k)
+        for (int i = 0; i < k; ++i)
+            if ((tri >> (k * (k + 1) / 2 + i)) & 1u) { r[i][k] = true; r[k][i] = true; }
+    for (int m = 0; m < d; ++m)
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j)
+                if (r[i][m] && r[m][j]) r[i][j] = true;
+    u64 out = 0;
+    for (int j = 0; j < d; ++j)
+        for (int i = 0; i < d; ++i)
+            if (r[i][j]) out |= 1ull << (i + d * j);
+    return out;
+}
+template <int D, u64 CM> struct Pat {
+    static constexpr int nnz = cx_popc(CM);
+    static constexpr bool full = (CM == full_cmask<D>());
+    __host__ __device__ static constexpr bool has(int i, int j) { return (CM >> (i + D * j)) & 1ull; }
+    __host__ __device__ static constexpr int idx(int i, int j) { return full ? (i + D * j) : cx_popc(CM & ((1ull << (i + D * j)) - 1ull)); }
+};
+// run-time versions (warp-uniform mask from DevProblem)
+__device__ __forceinline__ bool pat_has(u64 cm, int d, int i, int j) { return (cm >> (i + d * j)) & 1ull; }
+__device__ __forceinline__ int pat_idx(u64 cm, int d, int i, int j) { return __popcll(cm & ((1ull << (i + d * j)) - 1ull)); }

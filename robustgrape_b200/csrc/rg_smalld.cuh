@@ -301,7 +301,7 @@ __device__ __forceinline__ void horner_fo_tri(const cplx (&ta)[Tri<D>::n], const
 
 // Fused pass over a unitary step matrix U (shared memory): cp = U^dagger c and gn = g U.
 // Each loaded element feeds two complex FMAs (the two separate passes were LSU-wavefront bound).
-template <int D>
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void rewind_advance(const cplx* __restrict__ M, const cplx (&c)[D], const cplx (&g)[D],
                                                cplx (&cp)[D], cplx (&gn)[D]) {
 #pragma unroll
@@ -310,14 +310,15 @@ __device__ __forceinline__ void rewind_advance(const cplx* __restrict__ M, const
     for (int j = 0; j < D; ++j)
 #pragma unroll
         for (int i = 0; i < D; ++i) {
+            if (!Pat<D, CM>::has(i, j)) continue;
             const cplx u = M[i + D * j];
             cfma_conj(cp[j], u, c[i]);
             cfma(gn[j], g[i], u);
         }
 }
 
-// out = M * v   (M in shared memory, column-major)
-template <int D>
+// out = M * v   (M in shared memory, column-major; elements outside the pattern CM are skipped)
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void matvec(const cplx* __restrict__ M, const cplx (&v)[D], cplx (&out)[D]) {
 #pragma unroll
     for (int i = 0; i < D; ++i) out[i] = cmk(0.0, 0.0);
@@ -325,47 +326,47 @@ __device__ __forceinline__ void matvec(const cplx* __restrict__ M, const cplx (&
     for (int k = 0; k < D; ++k) {
         const cplx vk = v[k];
 #pragma unroll
-        for (int i = 0; i < D; ++i) cfma(out[i], M[i + D * k], vk);
+        for (int i = 0; i < D; ++i) if (Pat<D, CM>::has(i, k)) cfma(out[i], M[i + D * k], vk);
     }
 }
 // out += M * v
-template <int D>
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void matvec_acc(const cplx* __restrict__ M, const cplx (&v)[D], cplx (&out)[D]) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         const cplx vk = v[k];
 #pragma unroll
-        for (int i = 0; i < D; ++i) cfma(out[i], M[i + D * k], vk);
+        for (int i = 0; i < D; ++i) if (Pat<D, CM>::has(i, k)) cfma(out[i], M[i + D * k], vk);
     }
 }
 // out = M^dagger * v
-template <int D>
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void matvec_adj(const cplx* __restrict__ M, const cplx (&v)[D], cplx (&out)[D]) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         cplx a = cmk(0.0, 0.0);
 #pragma unroll
-        for (int k = 0; k < D; ++k) cfma_conj(a, M[k + D * i], v[k]);
+        for (int k = 0; k < D; ++k) if (Pat<D, CM>::has(k, i)) cfma_conj(a, M[k + D * i], v[k]);
         out[i] = a;
     }
 }
 // out = g * M   (row vector times matrix)
-template <int D>
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void vecmat(const cplx (&g)[D], const cplx* __restrict__ M, cplx (&out)[D]) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         cplx a = cmk(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < D; ++i) cfma(a, g[i], M[i + D * j]);
+        for (int i = 0; i < D; ++i) if (Pat<D, CM>::has(i, j)) cfma(a, g[i], M[i + D * j]);
         out[j] = a;
     }
 }
-template <int D>
+template <int D, u64 CM = full_cmask<D>()>
 __device__ __forceinline__ void vecmat_acc(const cplx (&g)[D], const cplx* __restrict__ M, cplx (&out)[D]) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) cfma(out[j], g[i], M[i + D * j]);
+        for (int i = 0; i < D; ++i) if (Pat<D, CM>::has(i, j)) cfma(out[j], g[i], M[i + D * j]);
     }
 }
 // Re(g . t)
@@ -435,7 +436,7 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             const int kn = min(k0 + kk + 1, k1 - 1);
             for (int i = 0; i < P.p; ++i) { xk[i] = xnext[i]; xnext[i] = xp[(size_t)kn * P.p + i]; }
         }
-        cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
+        cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * P.wsm;
 
         // ---- base matrix A = -i dt H0(x_k)
         fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
@@ -581,7 +582,7 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
-    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * P.wsm;
 
     fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
     __syncwarp(amask);
@@ -610,9 +611,9 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
             cplx y[D], da[D], db[D], dab[D];
             horner_so<D>(mA, mAl, mBe, mGa, l, m, y, da, db, dab, amask);
             if (live) {
-                cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * DD + l * D;
+                cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * P.wsm;
 #pragma unroll
-                for (int i = 0; i < D; ++i) dst[i] = dab[i];
+                for (int i = 0; i < D; ++i) if (pat_has(P.cmask, D, i, l)) dst[pat_idx(P.cmask, D, i, l)] = dab[i];
             }
             __syncwarp(amask);
         }
@@ -898,7 +899,7 @@ __device__ __forceinline__ double group_sum0(double v, int lane, int l, unsigned
 //            out1[(b*ne+e)*nx + ...] = (2/DD1) * Re{[g' dU w + h' dU c]/eps^2 + g' d2U c/eps2^2}
 //            (w and h' are built from raw, un-normalised differences, hence 1/eps^2)
 // additional-parameter variables go to addS[((b*(1+ne)+role)*a + j)*N + k] for a later sum over k.
-template <int D, bool ERR>
+template <int D, bool ERR, u64 CM>
 __global__ void __launch_bounds__(128)
 k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
        const cplx* __restrict__ Cb, const cplx* __restrict__ Wb, const cplx* __restrict__ Gb,
@@ -924,19 +925,36 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
     cplx* base = smem + (size_t)(warp * G + g) * k3_group_stride(D, nload);
     cplx* buf0 = base;
     cplx* buf1 = base + nload * DD;
+    typedef Pat<D, CM> PT;
+    // elements outside the pattern are never loaded: zero them once (they stay zero)
+    if (!PT::full) {
+        for (int s = 0; s < 2 * nload; ++s)
+#pragma unroll
+            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk(0.0, 0.0);
+        __syncwarp(amask);
+    }
 
     // stored objects this role needs: slot 0 = U, 1..nv = dU^v, [nv+1 = D_e, nv+2.. = d2U^{v,e}]
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * DD;
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    // compact offset of the first stored element of column l, and which rows are stored
+    int coff = 0; unsigned rows = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (PT::has(i, j)) { if (j < l) ++coff; if (j == l) rows |= 1u << i; }
     auto issue = [&](int k, cplx* dstbuf) {
-        const cplx* wsk = wsb + (size_t)k * P.nstore * DD;
+        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
         for (int s = 0; s < nload; ++s) {
             int obj = s;
             if (s == nv + 1) obj = 1 + nv + es;
             else if (s > nv + 1) obj = 1 + nv + ne + es * nv + (s - nv - 2);
-            const cplx* src = wsk + (size_t)obj * DD + l * D;
+            const cplx* src = wsk + (size_t)obj * PT::nnz + coff;
             cplx* dst = dstbuf + s * DD + l * D;
+            int r = 0;
 #pragma unroll
-            for (int i = 0; i < D; ++i) cp_async16(dst + i, src + i);
+            for (int i = 0; i < D; ++i)
+                if (PT::full || ((rows >> i) & 1u)) { cp_async16(dst + i, src + r); ++r; }
         }
         cp_async_commit();
     };
@@ -974,15 +992,15 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         const cplx* mZ = cur;
         const cplx* mDe = cur + (nv + 1) * DD;
         cplx cp[D], gn[D];
-        rewind_advance<D>(mZ, c, gr, cp, gn);           // c_{k-1} = U_k^dag c_k  and  g_{k-1} = g_k U_k in one pass
+        rewind_advance<D, CM>(mZ, c, gr, cp, gn);           // c_{k-1} = U_k^dag c_k  and  g_{k-1} = g_k U_k in one pass
         cplx wp[ERR ? D : 1];
         if (ERR) {
             cplx t[D];
-            matvec<D>(mDe, cp, t);                      // D_k c_{k-1}
+            matvec<D, CM>(mDe, cp, t);                      // D_k c_{k-1}
 #pragma unroll
             for (int i = 0; i < D; ++i) t[i] = csub(w[ERR ? i : 0], t[i]);
             cplx t2[D];
-            matvec_adj<D>(mZ, t, t2);                   // w_{k-1} = U_k^dag (w_k - D_k c_{k-1})
+            matvec_adj<D, CM>(mZ, t, t2);                   // w_{k-1} = U_k^dag (w_k - D_k c_{k-1})
 #pragma unroll
             for (int i = 0; i < (ERR ? D : 1); ++i) wp[i] = t2[i];
         }
@@ -991,7 +1009,7 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
             double s;
             {
                 cplx t[D];
-                matvec<D>(mDv, cp, t);                  // dU^v c_{k-1}
+                matvec<D, CM>(mDv, cp, t);                  // dU^v c_{k-1}
                 if (!ERR) {
                     s = redot<D>(gr, t) * scale0;
                 } else {
@@ -1005,10 +1023,10 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
                 cplx ww[D], t[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) ww[i] = wp[ERR ? i : 0];
-                matvec<D>(mDv, ww, t);                  // dU^v w_{k-1}
+                matvec<D, CM>(mDv, ww, t);                  // dU^v w_{k-1}
                 s += redot<D>(gr, t);
                 const cplx* mD2 = cur + (nv + 2 + v) * DD;
-                matvec<D>(mD2, cp, t);                  // d2U^{v,e} c_{k-1}
+                matvec<D, CM>(mD2, cp, t);                  // d2U^{v,e} c_{k-1}
                 s = f1 * s + f2 * redot<D>(gr, t);
             }
             s = group_sum0<D>(s, lane, l, amask);
@@ -1028,8 +1046,8 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
                 cplx hh[D], hn[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) hh[i] = hr[ERR ? i : 0];
-                vecmat<D>(hh, mZ, hn);
-                vecmat_acc<D>(gr, mDe, hn);
+                vecmat<D, CM>(hh, mZ, hn);
+                vecmat_acc<D, CM>(gr, mDe, hn);
 #pragma unroll
                 for (int i = 0; i < (ERR ? D : 1); ++i) { hr[i] = hn[i]; w[i] = wp[i]; }
             }

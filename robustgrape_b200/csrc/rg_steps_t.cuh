@@ -56,10 +56,12 @@ __device__ inline StagedPlan stage_plan(const DevProblem& P, const TriPlanDev& t
 // UMASK: compile-time superset of every position any matrix of this problem touches (pruned code and
 // registers for the rest); mA / mD: run-time (warp-uniform) masks of A and of the current dA, tested only
 // when UMASK is not the full triangle.
-template <int D, unsigned UMASK>
+template <int D, unsigned UMASK, int l>
 __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD,
-                                               int l, int m, cplx (&y)[D], cplx (&dl)[D]) {
+                                               int m, cplx (&y)[D], cplx (&dl)[D]) {
     constexpr bool MASKED = (UMASK != ((1u << Tri<D>::n) - 1u));
+    // column l of exp(A) is confined to the rows the closure pattern allows: y[k] == 0 elsewhere
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
     {
         const double inv = c_inv_j[m];
 #pragma unroll
@@ -87,16 +89,16 @@ __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], cons
             for (int i = 0; i <= k; ++i) {
                 const int pos = Tri<D>::idx(i, k);
                 if (!((UMASK >> pos) & 1u)) continue;
+                if (!PT::has(k, l) && !PT::has(i, l)) continue;      // both operands structurally zero in this column
                 if (!MASKED || ((mA >> pos) & 1u)) {
                     const cplx a = ta[pos];
-                    cfma(t[i], a, y[k]);
-                    cfma(u[i], a, dl[k]);
-                    if (i != k) { cfma_nconj(t[k], a, y[i]); cfma_nconj(u[k], a, dl[i]); }
+                    if (PT::has(k, l)) { cfma(t[i], a, y[k]); cfma(u[i], a, dl[k]); }
+                    if (i != k && PT::has(i, l)) { cfma_nconj(t[k], a, y[i]); cfma_nconj(u[k], a, dl[i]); }
                 }
                 if (!MASKED || ((mD >> pos) & 1u)) {
                     const cplx d = td[pos];
-                    cfma(u[i], d, cadd(y[k], dl[k]));
-                    if (i != k) cfma_nconj(u[k], d, cadd(y[i], dl[i]));
+                    if (PT::has(k, l)) cfma(u[i], d, cadd(y[k], dl[k]));
+                    if (i != k && PT::has(i, l)) cfma_nconj(u[k], d, cadd(y[i], dl[i]));
                 }
             }
         }
@@ -109,11 +111,31 @@ __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], cons
     }
 }
 
+template <int D, unsigned UMASK, int l>
+__device__ __forceinline__ void columns(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD, int m,
+                                        bool live, cplx* __restrict__ dstD, cplx* __restrict__ dstU) {
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    if constexpr (l < D) {
+        cplx y[D], dl[D];
+        horner_col_tri<D, UMASK, l>(ta, td, mA, mD, m, y, dl);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (PT::has(i, l)) {
+                    if (dstD) dstD[PT::idx(i, l)] = dl[i];
+                    if (dstU) dstU[PT::idx(i, l)] = y[i];
+                }
+        }
+        columns<D, UMASK, l + 1>(ta, td, mA, mD, m, live, dstD, dstU);
+    }
+}
+
 template <int D, unsigned UMASK>
 __global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 3)
 k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
           int* __restrict__ status) {
-    constexpr int DD = D * D, NP = Tri<D>::n;
+    constexpr int NP = Tri<D>::n;
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
     const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     const long long total = (long long)B * P.N;
@@ -125,7 +147,7 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
-    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * DD;
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * PT::nnz;
     const int nt = P.nterms, nv = P.nvar, ne = P.e, nfo = nv + ne;
 
     cplx ca[RG_T_MAX_TERMS], cd[RG_T_MAX_TERMS];     // (-i dt) * coefficient, value and difference
@@ -177,28 +199,14 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 1); m = 18; }
         }
         const unsigned mD = (nfo == 0) ? 0u : (o < nv ? tp.maskVar[o] : tp.maskErr[o - nv]);
-        // ---- columns
-        for (int l = 0; l < D; ++l) {
-            cplx y[D], dl[D];
-            horner_col_tri<D, UMASK>(ta, td, tp.maskA, mD, l, m, y, dl);
-            if (live) {
-                if (nfo > 0) {
-                    cplx* dst = wsk + (size_t)(1 + o) * DD + l * D;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) dst[i] = dl[i];
-                }
-                if (o == 0) {
-                    cplx* dst = wsk + l * D;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) dst[i] = y[i];
-                }
-            }
-        }
+        // ---- columns (unrolled: the pattern of each column is known at compile time)
+        columns<D, UMASK, 0>(ta, td, tp.maskA, mD, m, live, nfo > 0 ? wsk + (size_t)(1 + o) * PT::nnz : nullptr,
+                             o == 0 ? wsk : nullptr);
     }
 }
 
 // Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
-template <int D>
+template <int D, u64 CM>
 __global__ void __launch_bounds__(128)
 k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb) {
     constexpr int G = GroupInfo<D>::G;
@@ -220,15 +228,30 @@ k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ w
     cplx* buf0 = base;
     cplx* buf1 = base + nload * DD;
     cplx* wl = base + 2 * nload * DD + l * D;      // + e*DD, private columns
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * DD;
+    typedef Pat<D, CM> PT;
+    if (!PT::full) {
+        for (int s = 0; s < 2 * nload; ++s)
+#pragma unroll
+            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk(0.0, 0.0);
+        __syncwarp(amask);
+    }
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    int coff = 0; unsigned rows = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (PT::has(i, j)) { if (j < l) ++coff; if (j == l) rows |= 1u << i; }
     auto issue = [&](int k, cplx* dstbuf) {
-        const cplx* wsk = wsb + (size_t)k * P.nstore * DD;
+        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
         for (int s = 0; s < nload; ++s) {
             const int obj = (s == 0) ? 0 : (1 + nv + (s - 1));
-            const cplx* src = wsk + (size_t)obj * DD + l * D;
+            const cplx* src = wsk + (size_t)obj * PT::nnz + coff;
             cplx* dst = dstbuf + s * DD + l * D;
+            int r = 0;
 #pragma unroll
-            for (int i = 0; i < D; ++i) cp_async16(dst + i, src + i);
+            for (int i = 0; i < D; ++i)
+                if (PT::full || ((rows >> i) & 1u)) { cp_async16(dst + i, src + r); ++r; }
         }
         cp_async_commit();
     };
@@ -251,13 +274,13 @@ k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ w
                 cplx w[D], wn[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) w[i] = wl[e * DD + i];
-                matvec<D>(cur, w, wn);
-                matvec_acc<D>(cur + (1 + e) * DD, q, wn);
+                matvec<D, CM>(cur, w, wn);
+                matvec_acc<D, CM>(cur + (1 + e) * DD, q, wn);
 #pragma unroll
                 for (int i = 0; i < D; ++i) wl[e * DD + i] = wn[i];
             }
             cplx qn[D];
-            matvec<D>(cur, q, qn);
+            matvec<D, CM>(cur, q, qn);
 #pragma unroll
             for (int i = 0; i < D; ++i) q[i] = qn[i];
         }
