@@ -1,4 +1,175 @@
-// rg_analysis.cuh -- kernels for the analysis entry points (materialised unitary derivatives,
-// interaction-picture error operators, fidelity response, expectation values).
+// rg_analysis.cuh -- kernels for the analysis entry points:
+//   k_interaction_ops : calculate_interaction_error_operators (src/UnitaryCalculations.jl:180-204)
+//   k_response        : calculate_fidelity_response / _fft      (src/FidelityCalculations.jl:246-280, 306-343)
+//   k_expectation     : calculate_expectation_values            (src/FidelityCalculations.jl:368-390)
 #pragma once
-#include "rg_common.cuh"
+#include "rg_smalld.cuh"
+
+// O_k[e] = C_{k-1}^{-1} (Herr_e(k, x_k, x_add, eps)/eps) C_{k-1},  C_k = U_k C_{k-1}  (uses the cumulative
+// operator *before* step k, :194-200).  One group (D lanes of one warp) per pulse, sequential in time;
+// C^{-1} = C^dagger (Hermitian problems).  O layout: (d, d, N, e) column-major.
+template <int D>
+__global__ void __launch_bounds__(32)
+k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __restrict__ O, int* __restrict__ status) {
+    constexpr unsigned amask = (D == 32) ? 0xffffffffu : ((1u << D) - 1u);
+    constexpr int DD = D * D;
+    extern __shared__ cplx smem[];
+    const StagedDesc sd = stage_desc(P, reinterpret_cast<unsigned char*>(smem));
+    const int l = threadIdx.x;
+    if (l >= D) return;
+    cplx* base = smem + staged_desc_bytes(P.nterms, P.nent, D) / sizeof(cplx);
+    cplx* mA = base; cplx* mD = base + DD; cplx* mX = base + 2 * DD; cplx* mC = base + 3 * DD; cplx* mE = base + 4 * DD;
+    cplx* coef = base + 5 * DD;      // 2 * nterms
+    const int nt = P.nterms;
+    double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
+    for (int j = 0; j < P.a; ++j) xadd[j] = x[(size_t)P.p * P.N + j];
+    cplx c[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) c[i] = cmk(i == l ? 1.0 : 0.0, 0.0);
+    for (int t = l; t < nt; t += D) coef[nt + t] = cmk(0.0, 0.0);
+    __syncwarp(amask);
+    assemble_col<D>(sd.ents, sd.colptr, coef + nt, mD, l, true);     // zero perturbation: only U is needed
+    for (int k = 0; k < P.N; ++k) {
+        for (int i = 0; i < P.p; ++i) xk[i] = x[(size_t)k * P.p + i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) mC[i + D * l] = c[i];
+        __syncwarp(amask);
+        for (int e = 0; e < P.e; ++e) {
+            // Herr_e(eps) / eps : value coefficients without the -i dt factor
+            EvalCtx ec{xk, xadd, P.eps, P.table, P.N, k};
+            for (int t = l; t < nt; t += D) {
+                cplx b = cmk(0, 0), dl;
+                if (sd.terms[t].owner == e) term_coef(sd.terms[t], ec, RG_S_NONE, 0, 0.0, b, dl);
+                coef[t] = cscale(b, P.inv_eps);
+            }
+            __syncwarp(amask);
+            assemble_col<D>(sd.ents, sd.colptr, coef, mE, l);
+            __syncwarp(amask);
+            cplx t1[D], o[D];
+            matvec<D>(mE, c, t1);            // column l of Oerr C
+            matvec_adj<D>(mC, t1, o);        // column l of C^dagger Oerr C
+            cplx* dst = O + ((size_t)e * P.N + k) * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) dst[i] = o[i];
+            __syncwarp(amask);
+        }
+        fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
+        __syncwarp(amask);
+        assemble_col<D>(sd.ents, sd.colptr, coef, mA, l);
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
+        int m = taylor_degree(nrm * 1.001);
+        m = __reduce_max_sync(amask, m);
+        if (m == 99) { if (l == 0) atomicOr(status, 1); m = 18; }
+        __syncwarp(amask);
+        cplx y[D], dl[D];
+        horner_fo<D>(mA, mD, l, m, y, dl);
+#pragma unroll
+        for (int i = 0; i < D; ++i) mX[i + D * l] = y[i];
+        __syncwarp(amask);
+        cplx cn[D];
+        matvec<D>(mX, c, cn);
+#pragma unroll
+        for (int i = 0; i < D; ++i) c[i] = cn[i];
+        __syncwarp(amask);
+    }
+}
+
+// Response function for one (frequency, error source) per block:
+//   S = sum_{j=0}^{N-1} e^{-i w dt j} O_{j+1} ,  T = sum_{k} e^{+i w dt (k - 1 + shift)} O_k   (k = 1..N)
+//   R = dt^2 [ Re tr_mod(T S P)/D - Re tr_mod(T P S P)/(D(D+1)) - Re(tr_mod(T P) tr_mod(S P))/(D(D+1)) ]
+// shift = 1 reproduces calculate_fidelity_response (whose outer weight runs from 1, :269-271);
+// shift = 0 with w_n = 2 pi n / (M dt) reproduces calculate_fidelity_response_fft (fft / M*ifft, :328-339).
+// grid_mode: 0 = explicit frequencies; M > 0 = uniform FFT grid of M points (phases reduced exactly mod M).
+template <int D>
+__global__ void __launch_bounds__(128)
+k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restrict__ freqs, int first, int count,
+           int M, int shift, double* __restrict__ R) {
+    constexpr int DD = D * D;
+    constexpr int NS = 128 / DD > 0 ? 128 / DD : 1;     // time slices per block
+    __shared__ cplx sS[NS][DD], sT[NS][DD];
+    __shared__ cplx mS[DD], mT[DD];
+    const int f = blockIdx.x, e = blockIdx.y;
+    const int tid = threadIdx.x, el = tid % DD, sl = tid / DD;
+    const int n = first + f;
+    const double w = M > 0 ? 0.0 : freqs[n];
+    const double wdt = w * P.dt;
+    cplx s = cmk(0, 0), t = cmk(0, 0);
+    if (sl < NS) {
+        const cplx* Oe = O + (size_t)e * P.N * DD;
+        for (int j = sl; j < P.N; j += NS) {
+            double sn, cs;
+            if (M > 0) {
+                const long long r = ((long long)j * n) % M;
+                sincospi(2.0 * (double)r / (double)M, &sn, &cs);
+            } else {
+                sincos(wdt * (double)j, &sn, &cs);
+            }
+            const cplx o = Oe[(size_t)j * DD + el];
+            cfma(s, cmk(cs, -sn), o);        // e^{-i w dt j}
+            cfma(t, cmk(cs, sn), o);         // e^{+i w dt j}
+        }
+        sS[sl][el] = s; sT[sl][el] = t;
+    }
+    __syncthreads();
+    if (tid < DD) {
+        cplx a = cmk(0, 0), b = cmk(0, 0);
+        for (int q = 0; q < NS; ++q) { a = cadd(a, sS[q][tid]); b = cadd(b, sT[q][tid]); }
+        if (shift) {
+            double sn, cs;
+            sincos(wdt, &sn, &cs);
+            b = cmul(b, cmk(cs, sn));
+        }
+        mS[tid] = a; mT[tid] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // traces with P0 (tr_mod(A) = tr(P0 A)) and P = (P0 != 0); PP = P0 P is precomputed
+        const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
+        cplx SP[DD], TP[DD];
+        for (int j = 0; j < D; ++j)
+            for (int i = 0; i < D; ++i) {
+                cplx a = cmk(0, 0), b = cmk(0, 0);
+                for (int q = 0; q < D; ++q) { const double p = P.Pm[q + D * j]; a.x += mS[i + D * q].x * p; a.y += mS[i + D * q].y * p; b.x += mT[i + D * q].x * p; b.y += mT[i + D * q].y * p; }
+                SP[i + D * j] = a; TP[i + D * j] = b;
+            }
+        // t1 = tr(P0 T S P), t2 = tr(P0 T P S P), t3 = tr(P0 T P), t4 = tr(P0 S P)
+        cplx t1 = cmk(0, 0), t2 = cmk(0, 0), t3 = cmk(0, 0), t4 = cmk(0, 0);
+        const double* P0 = P.P0raw;
+        for (int a = 0; a < D; ++a)
+            for (int b = 0; b < D; ++b) {
+                const double p0 = P0[a + D * b];         // P0[a][b] multiplies X[b][a]
+                if (p0 == 0.0) continue;
+                cplx x1 = cmk(0, 0), x2 = cmk(0, 0);
+                for (int q = 0; q < D; ++q) { cfma(x1, mT[b + D * q], SP[q + D * a]); cfma(x2, TP[b + D * q], SP[q + D * a]); }
+                t1.x += p0 * x1.x; t1.y += p0 * x1.y;
+                t2.x += p0 * x2.x; t2.y += p0 * x2.y;
+                t3.x += p0 * TP[b + D * a].x; t3.y += p0 * TP[b + D * a].y;
+                t4.x += p0 * SP[b + D * a].x; t4.y += p0 * SP[b + D * a].y;
+            }
+        const double r = t1.x / Dt - t2.x / DD1 - (t3.x * t4.x - t3.y * t4.y) / DD1;
+        R[(size_t)e * count + f] = P.dt * P.dt * r;
+    }
+}
+
+// s[k,e] = tr(P0 O_k^e); out[k,e] = Re(dt * sum_{j<=k} s[j,e] / D)   (cumsum is linear in the trace)
+template <int D>
+__global__ void k_expectation(const DevProblem P, const cplx* __restrict__ O, double* __restrict__ out) {
+    constexpr int DD = D * D;
+    const int e = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const double* P0 = P.P0raw;
+    cplx acc[DD];
+    for (int i = 0; i < DD; ++i) acc[i] = cmk(0, 0);
+    for (int k = 0; k < P.N; ++k) {
+        const cplx* o = O + ((size_t)e * P.N + k) * DD;
+        double tr = 0.0;
+        for (int j = 0; j < D; ++j)
+            for (int i = 0; i < D; ++i) {
+                acc[i + D * j] = cadd(acc[i + D * j], o[i + D * j]);     // cumsum of the operators (:374)
+                tr += P0[j + D * i] * acc[i + D * j].x;                  // Re tr(P0 S) = sum P0[j][i] Re S[i][j]
+            }
+        out[(size_t)e * P.N + k] = P.dt * tr / P.Dtr;
+    }
+}

@@ -25,6 +25,8 @@ struct rg_ctx {
     int sm_count = 148;
     size_t ws_limit = (size_t)64 << 30;
     // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
+    int host_slabs = 4;                               // RG_HOST_SLABS (upper bound; slabs hold >= 2048 pulses)
     bool timing = false;
     struct Span { int kernel; cudaEvent_t e0, e1; };
     std::vector<Span> spans;
@@ -71,7 +73,7 @@ struct rg_problem {
     double tri_density = 1.0;
     unsigned tri_union = 0;   // union of all structural masks
     // workspaces
-    DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2;
+    DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2, dO, dFreq;
     int has_target = 0;
 };
 
@@ -120,6 +122,9 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     inv[0] = 0.0;
     for (int j = 1; j < 32; ++j) inv[j] = 1.0 / j;
     cudaMemcpyToSymbol(c_inv_j, inv, sizeof(inv));
+    if (const char* s = getenv("RG_HOST_SLABS")) c->host_slabs = std::max(1, atoi(s));
+    cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (const char* s = getenv("RG_WS_LIMIT_GB")) c->ws_limit = (size_t)atof(s) * ((size_t)1 << 30);
     if (cudaGetLastError() != cudaSuccess) { g_global_err = "context initialisation failed"; delete c; return RG_ERR_CUDA; }
     *out = c;
@@ -130,6 +135,8 @@ extern "C" void rg_ctx_destroy(rg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     delete c;
@@ -317,7 +324,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
             PP[i + d * j] = s; PPt[j + d * i] = s;
         }
     P.Dtr = tr;
-    P.PP = upload(pr, PP); P.PPt = upload(pr, PPt); P.Pm = upload(pr, Pm);
+    P.PP = upload(pr, PP); P.PPt = upload(pr, PPt); P.Pm = upload(pr, Pm); P.P0raw = upload(pr, P0);
     P.ntab = desc->ntable_cols;
     std::vector<double> tab;
     if (desc->table && desc->ntable_cols > 0) tab.assign(desc->table, desc->table + (size_t)desc->ntable_cols * P.N);
@@ -377,7 +384,7 @@ extern "C" void rg_problem_destroy(rg_problem* pr) {
     cudaSetDevice(pr->ctx->device);
     for (void* p : pr->owned) cudaFree(p);
     DevBuf* bufs[] = {&pr->ws, &pr->Qb, &pr->Wlb, &pr->Cb, &pr->Wb, &pr->Gb, &pr->G1b, &pr->H1b, &pr->F, &pr->F2,
-                      &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2};
+                      &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq};
     for (DevBuf* b : bufs) b->release();
     delete pr;
 }
@@ -646,7 +653,21 @@ extern "C" int rg_cost_and_grad_batch_dev(rg_problem* pr, int32_t B, const doubl
     return run_dev(pr, B, dX, 1, err_coeff, dcost, dgrad, nullptr, nullptr);
 }
 
-// Host-buffer entry points: H2D, run, D2H, synchronise.
+// Host-buffer entry points.  The batch is cut into slabs and pipelined over three streams:
+// H2D of slab i+1 and D2H of slab i-1 overlap the kernels of slab i (full-duplex PCIe), so the
+// end-to-end time approaches max(copy-in, compute, copy-out) instead of their sum.
+struct SlabPipe {
+    rg_ctx* ctx; int nslab, per; std::vector<cudaEvent_t> ev;
+    SlabPipe(rg_ctx* c, int B) : ctx(c) {
+        nslab = std::max(1, std::min(c->host_slabs, B / 2048));
+        per = (B + nslab - 1) / nslab;
+        nslab = (B + per - 1) / per;
+        ev.resize(2 * nslab);
+        for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    ~SlabPipe() { for (auto& e : ev) cudaEventDestroy(e); }
+};
+
 extern "C" int rg_fidelity_and_derivatives_batch(rg_problem* pr, int32_t B, const double* X, double* F, double* F_dx,
                                                  double* F_d2err, double* F_d2err_dx) {
     if (!pr) return RG_ERR_INVALID;
@@ -660,14 +681,27 @@ extern "C" int rg_fidelity_and_derivatives_batch(rg_problem* pr, int32_t B, cons
                  tot = oF2dx + (F_d2err_dx ? B * ne * nx : 0);
     if (pr->dX.ensure(B * nx * 8) || pr->dOut.ensure(std::max<size_t>(16, tot * 8))) RG_FAIL(ctx, RG_ERR_NOMEM, "device staging allocation failed");
     double* o = pr->dOut.as<double>();
-    CU(ctx, cudaMemcpyAsync(pr->dX.p, X, B * nx * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = run_dev(pr, B, pr->dX.as<double>(), 0, nullptr, o + oF, F_dx ? o + oFdx : nullptr, o + oF2,
-                     F_d2err_dx ? o + oF2dx : nullptr);
-    if (rc) return rc;
-    if (F) CU(ctx, cudaMemcpyAsync(F, o + oF, B * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (F_dx) CU(ctx, cudaMemcpyAsync(F_dx, o + oFdx, B * nx * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (F_d2err && ne) CU(ctx, cudaMemcpyAsync(F_d2err, o + oF2, B * ne * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (F_d2err_dx && ne) CU(ctx, cudaMemcpyAsync(F_d2err_dx, o + oF2dx, B * ne * nx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    double* dX = pr->dX.as<double>();
+    SlabPipe sp(ctx, B);
+    // order the copy streams after whatever is already queued on the compute stream
+    CU(ctx, cudaEventRecord(sp.ev[0], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_in, sp.ev[0], 0));
+    for (int s = 0; s < sp.nslab; ++s) {
+        const size_t b0 = (size_t)s * sp.per, bs = std::min<size_t>(sp.per, B - b0);
+        CU(ctx, cudaMemcpyAsync(dX + b0 * nx, X + b0 * nx, bs * nx * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaEventRecord(sp.ev[2 * s], ctx->s_in));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, sp.ev[2 * s], 0));
+        int rc = run_dev(pr, (int)bs, dX + b0 * nx, 0, nullptr, o + oF + b0, F_dx ? o + oFdx + b0 * nx : nullptr,
+                         o + oF2 + b0 * ne, F_d2err_dx ? o + oF2dx + b0 * ne * nx : nullptr);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(ctx, cudaEventRecord(sp.ev[2 * s + 1], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->s_out, sp.ev[2 * s + 1], 0));
+        if (F) CU(ctx, cudaMemcpyAsync(F + b0, o + oF + b0, bs * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (F_dx) CU(ctx, cudaMemcpyAsync(F_dx + b0 * nx, o + oFdx + b0 * nx, bs * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (F_d2err && ne) CU(ctx, cudaMemcpyAsync(F_d2err + b0 * ne, o + oF2 + b0 * ne, bs * ne * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (F_d2err_dx && ne) CU(ctx, cudaMemcpyAsync(F_d2err_dx + b0 * ne * nx, o + oF2dx + b0 * ne * nx, bs * ne * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->s_out));
     return rg_ctx_synchronize(ctx);
 }
 
@@ -682,11 +716,23 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
     const size_t nx = P.nx;
     if (pr->dX.ensure(B * nx * 8) || pr->dOut.ensure((B + B * nx) * 8)) RG_FAIL(ctx, RG_ERR_NOMEM, "device staging allocation failed");
     double* o = pr->dOut.as<double>();
-    CU(ctx, cudaMemcpyAsync(pr->dX.p, X, B * nx * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = run_dev(pr, B, pr->dX.as<double>(), 1, err_coeff, o, o + B, nullptr, nullptr);
-    if (rc) return rc;
-    CU(ctx, cudaMemcpyAsync(cost, o, B * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(grad, o + B, B * nx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    double* dX = pr->dX.as<double>();
+    SlabPipe sp(ctx, B);
+    CU(ctx, cudaEventRecord(sp.ev[0], ctx->stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_in, sp.ev[0], 0));
+    for (int s = 0; s < sp.nslab; ++s) {
+        const size_t b0 = (size_t)s * sp.per, bs = std::min<size_t>(sp.per, B - b0);
+        CU(ctx, cudaMemcpyAsync(dX + b0 * nx, X + b0 * nx, bs * nx * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaEventRecord(sp.ev[2 * s], ctx->s_in));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, sp.ev[2 * s], 0));
+        int rc = run_dev(pr, (int)bs, dX + b0 * nx, 1, err_coeff, o + b0, o + B + b0 * nx, nullptr, nullptr);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(ctx, cudaEventRecord(sp.ev[2 * s + 1], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->s_out, sp.ev[2 * s + 1], 0));
+        CU(ctx, cudaMemcpyAsync(cost + b0, o + b0, bs * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpyAsync(grad + b0 * nx, o + B + b0 * nx, bs * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->s_out));
     return rg_ctx_synchronize(ctx);
 }
 

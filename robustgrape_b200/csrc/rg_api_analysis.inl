@@ -39,19 +39,116 @@ extern "C" int rg_unitary_and_derivatives(rg_problem* pr, const double*, double*
     if (!pr) return RG_ERR_INVALID;
     RG_FAIL(pr->ctx, RG_ERR_UNSUPPORTED, "rg_unitary_and_derivatives: not implemented yet");
 }
-extern "C" int rg_interaction_error_operators(rg_problem* pr, const double*, double*) {
-    if (!pr) return RG_ERR_INVALID;
-    RG_FAIL(pr->ctx, RG_ERR_UNSUPPORTED, "rg_interaction_error_operators: not implemented yet");
+// ---- interaction-picture error operators on the device (shared by the three analysis entry points)
+template <int D>
+static int launch_interaction(rg_problem* pr, const double* dx, cplx* dO) {
+    rg_ctx* ctx = pr->ctx;
+    const DevProblem& P = pr->dp;
+    const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(5 * D * D + 2 * P.nterms) * sizeof(cplx);
+    int rc = set_smem(ctx, k_interaction_ops<D>, smem);
+    if (rc) return rc;
+    KTimer kt(ctx, RG_K_ANALYSIS);
+    k_interaction_ops<D><<<1, 32, smem, ctx->stream>>>(P, dx, dO, ctx->d_status);
+    return RG_OK;
 }
-extern "C" int rg_fidelity_response(rg_problem* pr, const double*, const double*, int32_t, int32_t, int32_t, double*) {
-    if (!pr) return RG_ERR_INVALID;
-    RG_FAIL(pr->ctx, RG_ERR_UNSUPPORTED, "rg_fidelity_response: not implemented yet");
+static int interaction_on_device(rg_problem* pr, const double* x) {
+    rg_ctx* ctx = pr->ctx;
+    const DevProblem& P = pr->dp;
+    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported yet");
+    if (P.e == 0) return RG_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (pr->dX.ensure((size_t)P.nx * 8) || pr->dO.ensure((size_t)P.d * P.d * P.N * P.e * sizeof(cplx))) RG_FAIL(ctx, RG_ERR_NOMEM, "device allocation failed");
+    CU(ctx, cudaMemcpyAsync(pr->dX.p, x, (size_t)P.nx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    switch (P.d) {
+#define RG_CASE(D) case D: return launch_interaction<D>(pr, pr->dX.as<double>(), pr->dO.as<cplx>());
+        RG_CASE(2) RG_CASE(3) RG_CASE(4) RG_CASE(5) RG_CASE(6) RG_CASE(7) RG_CASE(8) RG_CASE(9)
+#undef RG_CASE
+    default: break;
+    }
+    RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "unsupported ndim");
 }
-extern "C" int rg_fidelity_response_fft(rg_problem* pr, const double*, int32_t, double*, double*) {
+
+extern "C" int rg_interaction_error_operators(rg_problem* pr, const double* x, double* O) {
     if (!pr) return RG_ERR_INVALID;
-    RG_FAIL(pr->ctx, RG_ERR_UNSUPPORTED, "rg_fidelity_response_fft: not implemented yet");
+    rg_ctx* ctx = pr->ctx;
+    if (!x || (!O && pr->dp.e > 0)) RG_FAIL(ctx, RG_ERR_INVALID, "null argument");
+    int rc = interaction_on_device(pr, x);
+    if (rc) return rc;
+    const DevProblem& P = pr->dp;
+    if (P.e > 0) CU(ctx, cudaMemcpyAsync(O, pr->dO.p, (size_t)P.d * P.d * P.N * P.e * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    return rg_ctx_synchronize(ctx);
 }
-extern "C" int rg_expectation_values(rg_problem* pr, const double*, double*) {
+
+template <int D>
+static int launch_response(rg_problem* pr, const double* dfreqs, int first, int count, int M, int shift, double* dR) {
+    rg_ctx* ctx = pr->ctx;
+    KTimer kt(ctx, RG_K_ANALYSIS);
+    dim3 grid(count, pr->dp.e);
+    k_response<D><<<grid, 128, 0, ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dfreqs, first, count, M, shift, dR);
+    return RG_OK;
+}
+static int response_common(rg_problem* pr, const double* x, const double* freqs, int nfreq, int first, int count, int M,
+                           int shift, double* R) {
+    rg_ctx* ctx = pr->ctx;
+    const DevProblem& P = pr->dp;
+    if (!pr->has_target) RG_FAIL(ctx, RG_ERR_INVALID, "problem has no projector");
+    if (count <= 0 || P.e == 0) return RG_OK;
+    int rc = interaction_on_device(pr, x);
+    if (rc) return rc;
+    if (pr->dOut.ensure((size_t)count * P.e * 8) || pr->dFreq.ensure(std::max<size_t>(16, (size_t)nfreq * 8))) RG_FAIL(ctx, RG_ERR_NOMEM, "device allocation failed");
+    if (freqs) CU(ctx, cudaMemcpyAsync(pr->dFreq.p, freqs, (size_t)nfreq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    switch (P.d) {
+#define RG_CASE(D) case D: rc = launch_response<D>(pr, pr->dFreq.as<double>(), first, count, M, shift, pr->dOut.as<double>()); break;
+        RG_CASE(2) RG_CASE(3) RG_CASE(4) RG_CASE(5) RG_CASE(6) RG_CASE(7) RG_CASE(8) RG_CASE(9)
+#undef RG_CASE
+    default: RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "unsupported ndim");
+    }
+    if (rc) return rc;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(R, pr->dOut.p, (size_t)count * P.e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return rg_ctx_synchronize(ctx);
+}
+
+extern "C" int rg_fidelity_response(rg_problem* pr, const double* x, const double* freqs, int32_t nfreq, int32_t first,
+                                    int32_t count, double* R) {
     if (!pr) return RG_ERR_INVALID;
-    RG_FAIL(pr->ctx, RG_ERR_UNSUPPORTED, "rg_expectation_values: not implemented yet");
+    if (!x || !freqs || !R || first < 0 || count < 0 || first + count > nfreq) RG_FAIL(pr->ctx, RG_ERR_INVALID, "bad frequency range");
+    return response_common(pr, x, freqs, nfreq, first, count, 0, 1, R);
 }
+
+extern "C" int rg_fidelity_response_fft(rg_problem* pr, const double* x, int32_t oversampling, double* R, double* freqs_out) {
+    if (!pr) return RG_ERR_INVALID;
+    if (!x || !R || oversampling < 1) RG_FAIL(pr->ctx, RG_ERR_INVALID, "bad arguments");
+    const DevProblem& P = pr->dp;
+    const int M = P.N * oversampling;
+    if (freqs_out) for (int n = 0; n < M; ++n) freqs_out[n] = (2.0 * M_PI / (M * P.dt)) * n;      // :341
+    return response_common(pr, x, nullptr, 0, 0, M, M, 0, R);
+}
+
+template <int D>
+static int launch_expectation(rg_problem* pr, double* dOut) {
+    KTimer kt(pr->ctx, RG_K_ANALYSIS);
+    k_expectation<D><<<pr->dp.e, 32, 0, pr->ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dOut);
+    return RG_OK;
+}
+extern "C" int rg_expectation_values(rg_problem* pr, const double* x, double* out) {
+    if (!pr) return RG_ERR_INVALID;
+    rg_ctx* ctx = pr->ctx;
+    const DevProblem& P = pr->dp;
+    if (!x || (!out && P.e > 0)) RG_FAIL(ctx, RG_ERR_INVALID, "null argument");
+    if (!pr->has_target) RG_FAIL(ctx, RG_ERR_INVALID, "problem has no projector");
+    if (P.e == 0) return RG_OK;
+    int rc = interaction_on_device(pr, x);
+    if (rc) return rc;
+    if (pr->dOut.ensure((size_t)P.N * P.e * 8)) RG_FAIL(ctx, RG_ERR_NOMEM, "device allocation failed");
+    switch (P.d) {
+#define RG_CASE(D) case D: rc = launch_expectation<D>(pr, pr->dOut.as<double>()); break;
+        RG_CASE(2) RG_CASE(3) RG_CASE(4) RG_CASE(5) RG_CASE(6) RG_CASE(7) RG_CASE(8) RG_CASE(9)
+#undef RG_CASE
+    default: RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "unsupported ndim");
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, pr->dOut.p, (size_t)P.N * P.e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return rg_ctx_synchronize(ctx);
+}
+

@@ -30,6 +30,7 @@ struct DevProblem {
     const double* PP;    // P0 * P      (d x d, column-major, real)
     const double* PPt;   // (P0 * P)^T
     const double* Pm;    // P = (P0 != 0)
+    const double* P0raw; // the projector itself
     double Dtr;          // tr(P0)
     int nvar;            // perturbation variables: main 0..p-1, then additional params H depends on
     int var_space[RG_MAX_VARS], var_index[RG_MAX_VARS];

@@ -176,3 +176,63 @@ def test_optimize_wrapper_reaches_high_fidelity(gpu_ctx):
         additional_parameters={"f_abstol": 1e-15, "g_tol": 3e-10})
     res = rg.optimize_fidelity_and_error_sources(fp, prm)
     assert 1 - rg.calculate_fidelity_and_derivatives(fp, res.x)[0] < 1e-6
+
+
+# ---- analysis entry points ---------------------------------
+def _analysis_case(model="symmetric_blockaded", N=60):
+    fp = cz_problem(N, 7.613 * N / 500, ("amp", "freq"), model)
+    x = random_pulse(fp, 1, 21)
+    return fp, x
+
+
+@pytest.mark.parametrize("model", ["symmetric_blockaded", "full_blockaded"])
+def test_interaction_error_operators(gpu_ctx, model):
+    """reference src/UnitaryCalculations.jl:180-204; well-conditioned (no finite difference): 1e-11 relative."""
+    fp, x = _analysis_case(model)
+    got = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
+    ref = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max()
+
+
+def test_fidelity_response_direct_and_sharded(gpu_ctx):
+    """reference src/FidelityCalculations.jl:246-280, incl. the 0-based-sum / 1-based-weight phase quirk."""
+    fp, x = _analysis_case()
+    freqs = np.linspace(0, 3, 17)
+    ref = ro.calculate_fidelity_response(fp, x, freqs)
+    got = rg.calculate_fidelity_response(fp, x, freqs)
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+    # frequency shards (multi-GPU partitioning of the grid) reproduce the rows of the full sweep
+    a = rg.calculate_fidelity_response(fp, x, freqs, first=0, count=9)
+    b = rg.calculate_fidelity_response(fp, x, freqs, first=9, count=8)
+    assert np.array_equal(np.vstack([a, b]), got)
+
+
+def test_fidelity_response_fft(gpu_ctx):
+    """reference src/FidelityCalculations.jl:306-343 (on the GPU a direct DFT on the uniform grid)."""
+    fp, x = _analysis_case(N=40)
+    ref, fref = ro.calculate_fidelity_response_fft(fp, x, oversampling=3)
+    got, fgot = rg.calculate_fidelity_response_fft(fp, x, oversampling=3)
+    assert got.shape == (120, 2)
+    assert np.allclose(fgot, fref, rtol=1e-15, atol=0)
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+
+
+def test_expectation_values(gpu_ctx):
+    """reference src/FidelityCalculations.jl:368-390 (integrated Rydberg population, examples/time_optimal_cz.jl:70-74)."""
+    fp = cz_problem(80, 7.613, ("decay",))
+    x = random_pulse(fp, 1, 5)
+    ref = ro.calculate_expectation_values(fp, x)
+    got = rg.calculate_expectation_values(fp, x)
+    assert got.shape == (80, 1)
+    assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_response_at_zero_frequency_matches_sensitivity(gpu_ctx):
+    """reference test/runtests.jl:531-619 and examples/time_optimal_cz.jl:82-84: -F_d2err == 2 R(0), all on the GPU."""
+    fp, x = _analysis_case(N=200)
+    s = rg.calculate_fidelity_and_derivatives(fp, x)[2]
+    R = rg.calculate_fidelity_response(fp, x, np.array([0.0, 1.0]))
+    Rf, _ = rg.calculate_fidelity_response_fft(fp, x, oversampling=2)
+    assert np.allclose(-s, 2 * R[0], rtol=1e-3, atol=1e-3)
+    assert np.allclose(-s, 2 * Rf[0], rtol=1e-3, atol=1e-3)
