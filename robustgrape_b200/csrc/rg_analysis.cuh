@@ -59,12 +59,32 @@ k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __rest
         double nrm = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
-        int m = taylor_degree(nrm * 1.001);
-        m = __reduce_max_sync(amask, m);
-        if (m == 99) { if (l == 0) atomicOr(status, 1); m = 18; }
+        int m, sq;
+        {
+            unsigned long long nb = __double_as_longlong(nrm * 1.001);
+            nb = __reduce_max_sync(amask, (unsigned)(nb >> 32));
+            expm_plan(__longlong_as_double((long long)((nb + 1ull) << 32)), m, sq);
+            if (m == 99) { if (l == 0) atomicOr(status, 1); m = 12; }
+        }
+        if (sq) {
+            const double sc = scalbn(1.0, -sq);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mA[i + D * l] = cscale(mA[i + D * l], sc);
+        }
         __syncwarp(amask);
         cplx y[D], dl[D];
         horner_fo<D>(mA, mD, l, m, y, dl);
+        for (int q2 = 0; q2 < sq; ++q2) {
+            __syncwarp(amask);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mX[i + D * l] = y[i];
+            __syncwarp(amask);
+            cplx yn[D];
+            matvec<D>(mX, y, yn);
+#pragma unroll
+            for (int i = 0; i < D; ++i) y[i] = yn[i];
+        }
+        __syncwarp(amask);
 #pragma unroll
         for (int i = 0; i < D; ++i) mX[i + D * l] = y[i];
         __syncwarp(amask);

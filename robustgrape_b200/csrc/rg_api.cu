@@ -73,7 +73,7 @@ struct rg_problem {
     double tri_density = 1.0;
     unsigned tri_union = 0;   // union of all structural masks
     // workspaces
-    DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2, dO, dFreq;
+    DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2, dO, dFreq, dM;
     int has_target = 0;
 };
 
@@ -156,9 +156,12 @@ extern "C" int rg_ctx_synchronize(rg_ctx* c) {
     CU(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (*c->h_status != 0) {
+        const int fl = *c->h_status;
         *c->h_status = 0;
         cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream);
-        RG_FAIL(c, RG_ERR_NORM, "||dt*H||_1 exceeds the range of the Taylor propagator (1.1); reduce dt");
+        if (fl & 1) RG_FAIL(c, RG_ERR_NORM, "||dt*H||_1 needs more than %d squarings; reduce dt", RG_MAX_SQUARINGS);
+        RG_FAIL(c, RG_ERR_NORM, "||dt*H||_1 > 1.1 needs scaling-and-squaring, which the thread-per-step fast path does not do: "
+                                "host-buffer entry points fall back automatically; with device buffers set RG_GROUP=1");
     }
     return RG_OK;
 }
@@ -384,7 +387,7 @@ extern "C" void rg_problem_destroy(rg_problem* pr) {
     cudaSetDevice(pr->ctx->device);
     for (void* p : pr->owned) cudaFree(p);
     DevBuf* bufs[] = {&pr->ws, &pr->Qb, &pr->Wlb, &pr->Cb, &pr->Wb, &pr->Gb, &pr->G1b, &pr->H1b, &pr->F, &pr->F2,
-                      &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq};
+                      &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq, &pr->dM};
     for (DevBuf* b : bufs) b->release();
     delete pr;
 }
@@ -537,7 +540,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         KTimer kt(ctx, RG_K_SCAN);
         k_scan<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, nc, pr->Qb.as<cplx>(), pr->Wlb.as<cplx>(), pr->Cb.as<cplx>(),
                                                pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(),
-                                               iF, iF2, pr->addT.as<double>());
+                                               iF, iF2, pr->addT.as<double>(), 0, nullptr, nullptr);
     }
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     // mode 1 with no error sources writes -F_dx straight into grad
@@ -702,7 +705,12 @@ extern "C" int rg_fidelity_and_derivatives_batch(rg_problem* pr, int32_t B, cons
         if (F_d2err_dx && ne) CU(ctx, cudaMemcpyAsync(F_d2err_dx + b0 * ne * nx, o + oF2dx + b0 * ne * nx, bs * ne * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     CU(ctx, cudaStreamSynchronize(ctx->s_out));
-    return rg_ctx_synchronize(ctx);
+    int rcs = rg_ctx_synchronize(ctx);
+    if (rcs == RG_ERR_NORM && pr->tri_ok && !pr->force_group) {      // fast path out of range: general kernels square
+        pr->force_group = 1;
+        return rg_fidelity_and_derivatives_batch(pr, B, X, F, F_dx, F_d2err, F_d2err_dx);
+    }
+    return rcs;
 }
 
 extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X, const double* err_coeff,
@@ -733,7 +741,12 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
         CU(ctx, cudaMemcpyAsync(grad + b0 * nx, o + B + b0 * nx, bs * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     }
     CU(ctx, cudaStreamSynchronize(ctx->s_out));
-    return rg_ctx_synchronize(ctx);
+    int rcs = rg_ctx_synchronize(ctx);
+    if (rcs == RG_ERR_NORM && pr->tri_ok && !pr->force_group) {
+        pr->force_group = 1;
+        return rg_cost_and_grad_batch(pr, B, X, err_coeff, cost, grad);
+    }
+    return rcs;
 }
 
 #include "rg_api_analysis.inl"

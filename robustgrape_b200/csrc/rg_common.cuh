@@ -142,6 +142,20 @@ __device__ __forceinline__ int taylor_degree(double nrm) {
     if (nrm <= 1.10) return 18;
     return 99;   // needs scaling and squaring
 }
+// Scaling-and-squaring plan: exp(A) = (T_m(A / 2^s))^(2^s).  Above the Taylor range the matrix is scaled into
+// [0.155, 0.31] (degree 12) and squared s times; differences are squared with
+//   d(X^2) = dX (X + dX) + X dX     (exact: (X+dX)^2 - X^2)
+// so they stay free of cancellation.  s > RG_MAX_SQUARINGS is reported as RG_ERR_NORM.
+#define RG_MAX_SQUARINGS 24
+__device__ __forceinline__ void expm_plan(double nrm, int& m, int& s) {
+    m = taylor_degree(nrm); s = 0;
+    if (m == 99) {
+        s = (int)ceil(log2(nrm / 0.31));
+        if (s < 1) s = 1;
+        m = 12;
+        if (s > RG_MAX_SQUARINGS) { s = RG_MAX_SQUARINGS; m = 99; }
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // Structural pattern of the step matrices.  If H only couples certain pairs of levels, U = exp(-i dt H)

@@ -32,8 +32,9 @@ __host__ __device__ inline int rg_odd(int n) { return (n & 1) ? n : n + 1; }
 __host__ __device__ inline int k1_group_stride(int D, int nterms, int ne) {
     return rg_odd((4 + ne) * D * D + 2 * nterms);
 }
-__host__ __device__ inline int k1b_group_stride(int D, int nterms) { return rg_odd(4 * D * D + 4 * nterms); }
+__host__ __device__ inline int k1b_group_stride(int D, int nterms) { return rg_odd(5 * D * D + 4 * nterms); }
 __host__ __device__ inline int kagg_group_stride(int D, int ne) { return rg_odd((2 * (1 + ne) + ne) * D * D + 1); }
+__host__ __device__ inline int kmat_group_stride(int D, int nload) { return rg_odd((nload + 2) * D * D + 1); }
 __host__ __device__ inline int k2_group_stride(int D) { return rg_odd(14 * D * D + D + 1); }
 __host__ __device__ inline int k3_group_stride(int D, int nload) { return rg_odd(2 * nload * D * D + D + 1); }
 
@@ -445,9 +446,21 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
         double nrm = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
-        int m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
-        m = __reduce_max_sync(amask, m);
-        if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }
+        // Taylor degree and number of squarings, uniform across the warp
+        int m, sq;
+        {
+            nrm = nrm * 1.001 + 2.0 * P.eps2 * P.dt;
+            unsigned long long nb = __double_as_longlong(nrm);            // positive doubles order like integers
+            nb = __reduce_max_sync(amask, (unsigned)(nb >> 32));
+            expm_plan(__longlong_as_double((long long)((nb + 1ull) << 32)), m, sq);
+            if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 12; }
+        }
+        const double sc = sq ? scalbn(1.0, -sq) : 1.0;
+        if (sq) {
+            __syncwarp(amask);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mA[i + D * l] = cscale(mA[i + D * l], sc);
+        }
         cplx ta[TRI ? Tri<D>::n : 1];
         if (TRI) {
             __syncwarp(amask);
@@ -469,6 +482,10 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             }
             __syncwarp(amask);
             assemble_col<D>(sd.ents, sd.colptr, cf, mD, l, ghost);
+            if (sq) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) mD[i + D * l] = cscale(mD[i + D * l], sc);
+            }
             __syncwarp(amask);
             cplx y[D], dl[D];
             if (TRI) {
@@ -478,6 +495,22 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             } else {
                 horner_fo<D>(mA, mD, l, m, y, dl);
             }
+            // squarings: Y <- Y Y ;  Dl <- Dl (Y + Dl) + Y Dl   (mX holds Y, mD is free after the Horner pass)
+            for (int q2 = 0; q2 < sq; ++q2) {
+                __syncwarp(amask);
+#pragma unroll
+                for (int i = 0; i < D; ++i) { mX[i + D * l] = y[i]; mD[i + D * l] = dl[i]; }
+                __syncwarp(amask);
+                cplx yn[D], dn[D], sy[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) sy[i] = cadd(y[i], dl[i]);
+                matvec<D>(mX, y, yn);
+                matvec<D>(mD, sy, dn);
+                matvec_acc<D>(mX, dl, dn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) { y[i] = yn[i]; dl[i] = dn[i]; }
+            }
+            if (sq) __syncwarp(amask);
             if (st && nfo > 0) {
                 cplx* dst = wsk + (size_t)(1 + o) * DD + l * D;
 #pragma unroll
@@ -576,7 +609,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     cplx* mAl = base + DD;
     cplx* mBe = base + 2 * DD;
     cplx* mGa = base + 3 * DD;
-    cplx* coef = base + 4 * DD;     // 4 * nt
+    cplx* mY = base + 4 * DD;       // squaring scratch
+    cplx* coef = base + 5 * DD;     // 4 * nt
 
     const double* xp = X + (size_t)b * P.nx;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
@@ -590,14 +624,29 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
-    int m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
-    m = __reduce_max_sync(amask, m);
-    if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 18; }
+    int m, sq;
+    {
+        nrm = nrm * 1.001 + 2.0 * P.eps2 * P.dt;
+        unsigned long long nb = __double_as_longlong(nrm);
+        nb = __reduce_max_sync(amask, (unsigned)(nb >> 32));
+        expm_plan(__longlong_as_double((long long)((nb + 1ull) << 32)), m, sq);
+        if (m == 99) { if (lane == 0) atomicOr(status, 1); m = 12; }
+    }
+    const double sc = sq ? scalbn(1.0, -sq) : 1.0;
+    if (sq) {
+        __syncwarp(amask);
+#pragma unroll
+        for (int i = 0; i < D; ++i) mA[i + D * l] = cscale(mA[i + D * l], sc);
+    }
 
     for (int e = 0; e < ne; ++e) {
         fill_coefs<D>(P, sd.terms, coef + 2 * nt, VK_ERR, e, P.eps2, RG_S_NONE, 0, 0.0, xk, xadd, k, l);   // beta
         __syncwarp(amask);
         assemble_col<D>(sd.ents, sd.colptr, coef + 2 * nt, mBe, l);
+        if (sq) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) mBe[i + D * l] = cscale(mBe[i + D * l], sc);
+        }
         for (int v = 0; v < nv; ++v) {
             const int sp = P.var_space[v], ix = P.var_index[v];
             const double val = (sp == RG_S_MAIN) ? xk[ix] : xadd[ix];
@@ -607,9 +656,45 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
             __syncwarp(amask);
             assemble_col<D>(sd.ents, sd.colptr, coef + nt, mAl, l);
             assemble_col<D>(sd.ents, sd.colptr, coef + 3 * nt, mGa, l);
+            if (sq) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) { mAl[i + D * l] = cscale(mAl[i + D * l], sc); mGa[i + D * l] = cscale(mGa[i + D * l], sc); }
+            }
             __syncwarp(amask);
             cplx y[D], da[D], db[D], dab[D];
             horner_so<D>(mA, mAl, mBe, mGa, l, m, y, da, db, dab, amask);
+            if (sq) {
+                // squarings of the (value, da, db, dab) quadruple; beta (mBe) is saved in registers and restored
+                cplx be_save[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) be_save[i] = mBe[i + D * l];
+                for (int q2 = 0; q2 < sq; ++q2) {
+                    __syncwarp(amask);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { mY[i + D * l] = y[i]; mAl[i + D * l] = da[i]; mBe[i + D * l] = db[i]; mGa[i + D * l] = dab[i]; }
+                    __syncwarp(amask);
+                    cplx yn[D], an[D], bn[D], abn[D], t[D];
+                    // dab' = dab (Y+da+db+dab) + (Y+da+db) dab + da db + db da
+#pragma unroll
+                    for (int i = 0; i < D; ++i) t[i] = cadd(cadd(y[i], da[i]), cadd(db[i], dab[i]));
+                    matvec<D>(mGa, t, abn);
+                    matvec_acc<D>(mY, dab, abn); matvec_acc<D>(mAl, dab, abn); matvec_acc<D>(mBe, dab, abn);
+                    matvec_acc<D>(mAl, db, abn); matvec_acc<D>(mBe, da, abn);
+                    // da' = da (Y+da) + Y da ; db' likewise ; Y' = Y Y
+#pragma unroll
+                    for (int i = 0; i < D; ++i) t[i] = cadd(y[i], da[i]);
+                    matvec<D>(mAl, t, an); matvec_acc<D>(mY, da, an);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) t[i] = cadd(y[i], db[i]);
+                    matvec<D>(mBe, t, bn); matvec_acc<D>(mY, db, bn);
+                    matvec<D>(mY, y, yn);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { y[i] = yn[i]; da[i] = an[i]; db[i] = bn[i]; dab[i] = abn[i]; }
+                }
+                __syncwarp(amask);
+#pragma unroll
+                for (int i = 0; i < D; ++i) mBe[i + D * l] = be_save[i];
+            }
             if (live) {
                 cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * P.wsm;
 #pragma unroll
@@ -671,7 +756,10 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
        cplx* __restrict__ Cb, cplx* __restrict__ Wb, cplx* __restrict__ Gb, cplx* __restrict__ G1b, cplx* __restrict__ H1b,
        double* __restrict__ Fout,      // [B]
        double* __restrict__ F2out,     // [B][e]
-       double* __restrict__ addT)      // [B][1+e][a]  target-derivative parts of the x_add gradient
+       double* __restrict__ addT,      // [B][1+e][a]  target-derivative parts of the x_add gradient
+       int materialize,                // 1: co-state seeds are the identity (G = B_k, H' = dB_k/derr) and
+       cplx* __restrict__ Uout,        //    U = C_N        [B][d*d]            are written out
+       cplx* __restrict__ Eout)        //    E_e = W_N/eps  [B][e][d*d]
 {
     constexpr int G = GroupInfo<D>::G;
     constexpr unsigned amask = GroupInfo<D>::amask;
@@ -746,6 +834,54 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
             }
         }
         __syncwarp(amask);
+    }
+
+    if (materialize) {
+        if (live) {
+            cplx* dst = (role == 0) ? Uout + (size_t)b * DD + l * D : Eout + ((size_t)b * ne + es) * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) dst[i] = (role == 0) ? c[i] : cscale(w[i], P.inv_eps);
+        }
+        // backward with identity seeds
+        cplx gr[D], hr[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) { gr[j] = cmk(j == l ? 1.0 : 0.0, 0.0); hr[j] = cmk(0.0, 0.0); }
+        for (int ch = nc - 1; ch >= 0; --ch) {
+            if (live) {
+                if (role == 0) {
+                    cplx* dst = Gb + ((size_t)b * nc + ch) * DD + l * D;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dst[i] = gr[i];
+                } else {
+                    cplx* dst = G1b + (((size_t)b * ne + es) * nc + ch) * DD + l * D;
+                    cplx* dsh = H1b + (((size_t)b * ne + es) * nc + ch) * DD + l * D;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { dst[i] = gr[i]; dsh[i] = hr[i]; }
+                }
+            }
+            const cplx* q = Qb + ((size_t)b * nc + ch) * DD + l * D;
+            __syncwarp(amask);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mX[i + D * l] = q[i];
+            if (role > 0) {
+                const cplx* ww = Wlb + (((size_t)b * nc + ch) * ne + es) * DD + l * D;
+#pragma unroll
+                for (int i = 0; i < D; ++i) mW[i + D * l] = ww[i];
+            }
+            __syncwarp(amask);
+            cplx gn[D];
+            vecmat<D>(gr, mX, gn);
+            if (role > 0) {
+                cplx hn[D];
+                vecmat<D>(hr, mX, hn);
+                vecmat_acc<D>(gr, mW, hn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) hr[i] = hn[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) gr[i] = gn[i];
+        }
+        return;
     }
 
     // ---- fidelity algebra
@@ -1056,6 +1192,146 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         }
         __syncwarp(amask);
     }
+}
+
+
+// ======================================================================================
+// Materialising variant of the backward sweep: emits the matrices of calculate_unitary_and_derivatives
+// (src/UnitaryCalculations.jl:114-152) instead of contracting them.  Co-states come from k_scan run with
+// identity seeds, so gr = row l of B_k = U_N ... U_{k+1} and hr = row l of dB_k/derr (un-normalised).
+//   role 0     : U_dx[:,:,v,k]      = B_k dU^v C_{k-1} / eps
+//   role 1 + e : U_derr_dx[:,:,v,k,e] = [B_k dU^v W_{k-1} + V_k dU^v C_{k-1}] / eps^2 + B_k d2U^{v,e} C_{k-1} / eps2^2
+// Additional-parameter variables go to addM[((role*a + j)*N + k)*d*d ...] for a later sum over k.
+template <int D, u64 CM>
+__global__ void __launch_bounds__(128)
+k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
+              const cplx* __restrict__ Cb, const cplx* __restrict__ Wb, const cplx* __restrict__ Gb,
+              const cplx* __restrict__ G1b, const cplx* __restrict__ H1b,
+              cplx* __restrict__ U_dx, cplx* __restrict__ U_derr_dx, cplx* __restrict__ addM) {
+    constexpr int G = GroupInfo<D>::G;
+    constexpr unsigned amask = GroupInfo<D>::amask;
+    constexpr int DD = D * D;
+    typedef Pat<D, CM> PT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= G * D) return;
+    const int g = lane / D, l = lane - g * D;
+    long long item = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * G + g;
+    const bool live = item < nc;
+    if (!live) item = nc - 1;
+    const int ch = (int)item;
+    const int role = blockIdx.y, es = role - 1;
+    const int nv = P.nvar, ne = P.e;
+    const int nload = (role == 0) ? (1 + nv) : (2 + 2 * nv);
+    const int nload_max = (ne > 0) ? (2 + 2 * nv) : (1 + nv);
+
+    extern __shared__ cplx smem[];
+    cplx* base = smem + (size_t)(warp * G + g) * kmat_group_stride(D, nload_max);
+    cplx* mats = base;                         // nload matrices, dense d x d (zeros outside the pattern)
+    cplx* mB = base + nload_max * DD;
+    cplx* mV = mB + DD;
+    for (int s2 = 0; s2 < nload_max; ++s2)
+#pragma unroll
+        for (int i = 0; i < D; ++i) mats[s2 * DD + l * D + i] = cmk(0.0, 0.0);
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    cplx c[D], w[D], gr[D], hr[D];
+    {
+        const cplx* src = Cb + (size_t)ch * DD + l * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) { c[i] = src[i]; w[i] = cmk(0, 0); hr[i] = cmk(0, 0); }
+        if (role == 0) {
+            const cplx* sg = Gb + (size_t)ch * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) gr[i] = sg[i];
+        } else {
+            const size_t off = ((size_t)es * nc + ch) * DD + l * D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) { w[i] = Wb[off + i]; gr[i] = G1b[off + i]; hr[i] = H1b[off + i]; }
+        }
+    }
+    for (int kk = L - 1; kk >= 0; --kk) {
+        const bool ghost = (k0 + kk >= k1);
+        const int k = min(k0 + kk, k1 - 1);
+        __syncwarp(amask);
+        const cplx* wsk = ws + (size_t)k * P.nstore * PT::nnz;
+        for (int s2 = 0; s2 < nload; ++s2) {
+            int obj = s2;
+            if (s2 == nv + 1) obj = 1 + nv + es;
+            else if (s2 > nv + 1) obj = 1 + nv + ne + es * nv + (s2 - nv - 2);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (pat_has(CM, D, i, l)) mats[s2 * DD + l * D + i] = wsk[(size_t)obj * PT::nnz + pat_idx(CM, D, i, l)];
+        }
+        // rows of B_k and V_k for the left multiplications
+#pragma unroll
+        for (int j = 0; j < D; ++j) { mB[l + D * j] = gr[j]; mV[l + D * j] = hr[j]; }
+        __syncwarp(amask);
+        const cplx* mZ = mats;
+        const cplx* mDe = mats + (nv + 1) * DD;
+        cplx cp[D], gn[D], wp[D];
+        rewind_advance<D>(mZ, c, gr, cp, gn);
+        if (role > 0) {
+            cplx t[D];
+            matvec<D>(mDe, cp, t);
+#pragma unroll
+            for (int i = 0; i < D; ++i) t[i] = csub(w[i], t[i]);
+            matvec_adj<D>(mZ, t, wp);
+        }
+        for (int v = 0; v < nv; ++v) {
+            const cplx* mDv = mats + (1 + v) * DD;
+            cplx t1[D], out[D];
+            matvec<D>(mDv, cp, t1);
+            if (role == 0) {
+                matvec<D>(mB, t1, out);
+#pragma unroll
+                for (int i = 0; i < D; ++i) out[i] = cscale(out[i], P.inv_eps);
+            } else {
+                cplx t2[D], a1[D], a2[D];
+                matvec<D>(mDv, wp, t2);
+                matvec<D>(mB, t2, a1);
+                matvec_acc<D>(mV, t1, a1);
+                matvec<D>(mats + (nv + 2 + v) * DD, cp, t2);
+                matvec<D>(mB, t2, a2);
+#pragma unroll
+                for (int i = 0; i < D; ++i) out[i] = cadd(cscale(a1[i], P.inv_eps * P.inv_eps), cscale(a2[i], P.inv_eps2sq));
+            }
+            if (live && !ghost) {
+                cplx* dst;
+                if (P.var_space[v] == RG_S_MAIN) {
+                    const size_t m = (size_t)P.var_index[v] + (size_t)P.p * k;
+                    dst = (role == 0) ? U_dx + m * DD : U_derr_dx + (m + (size_t)P.p * P.N * es) * DD;
+                } else {
+                    dst = addM + (((size_t)role * P.a + P.var_index[v]) * P.N + k) * DD;
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[l * D + i] = out[i];
+            }
+        }
+        if (!ghost) {
+            if (role > 0) {
+                cplx hn[D];
+                vecmat<D>(hr, mZ, hn);
+                vecmat_acc<D>(gr, mDe, hn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) { hr[i] = hn[i]; w[i] = wp[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) { gr[i] = gn[i]; c[i] = cp[i]; }
+        }
+    }
+}
+// U_dx_add[:,:,j] / U_derr_dx_add[:,:,j,e] = sum over time of the per-step matrices (src/UnitaryCalculations.jl:119-121,140-151);
+// exact zero for additional parameters the Hamiltonian does not depend on.
+__global__ void k_reduce_add(const DevProblem P, const cplx* __restrict__ addM, cplx* __restrict__ U_dx_add, cplx* __restrict__ U_derr_dx_add) {
+    const int DD = P.d * P.d;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrole = 1 + P.e;
+    if (idx >= nrole * P.a * DD) return;
+    const int el = idx % DD, j = (idx / DD) % P.a, role = idx / (DD * P.a);
+    cplx s = cmk(0, 0);
+    if (P.add_var[j] >= 0)
+        for (int k = 0; k < P.N; ++k) s = cadd(s, addM[(((size_t)role * P.a + j) * P.N + k) * DD + el]);
+    if (role == 0) U_dx_add[(size_t)j * DD + el] = s;
+    else U_derr_dx_add[((size_t)j + (size_t)P.a * (role - 1)) * DD + el] = s;
 }
 
 // ======================================================================================

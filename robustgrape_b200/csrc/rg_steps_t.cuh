@@ -196,7 +196,7 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             }
             m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
             m = __reduce_max_sync(0xffffffffu, m);
-            if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 1); m = 18; }
+            if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 2); m = 18; }
         }
         const unsigned mD = (nfo == 0) ? 0u : (o < nv ? tp.maskVar[o] : tp.maskErr[o - nv]);
         // ---- columns (unrolled: the pattern of each column is known at compile time)

@@ -157,10 +157,25 @@ def test_api_shapes_and_asserts(gpu_ctx):
         rg.cost_and_gradient_batch(fp, np.zeros((11, 2)), [])
 
 
+@pytest.mark.parametrize("N,t0,errors,model", [(3, 40.0, ("amp", "freq"), "symmetric_blockaded"), (5, 300.0, ("amp",), "symmetric_blockaded"),
+                                               (4, 25.0, ("freq", "amp"), "full_blockaded"), (2, 2.5, (), "symmetric_blockaded")])
+def test_scaling_and_squaring(gpu_ctx, N, t0, errors, model):
+    """dt * ||H||_1 up to ~40: outside the Taylor range, handled by scaling-and-squaring of the (value, difference)
+    pairs.  Compared with the exact-semantics oracle (mpmath expm handles any norm) at 1e-9 of the largest
+    component -- each squaring doubles the relative rounding error."""
+    from oracle import exact_oracle as eo
+    fp = cz_problem(N, t0, errors, model)
+    x = random_pulse(fp, 1, 31)
+    got = rg.calculate_fidelity_and_derivatives(fp, x)
+    ex = eo.calculate_fidelity_and_derivatives(fp, x)
+    for k, g, e in zip(NAMES, got, ex):
+        assert relmax(g, e) < 1e-9, (k, relmax(g, e))
+
+
 def test_norm_out_of_range_is_reported(gpu_ctx):
-    fp = cz_problem(2, 40.0)        # dt * ||H|| ~ 14: outside the Taylor range
+    fp = cz_problem(1, 1e9)        # dt * ||H|| ~ 1e9: beyond RG_MAX_SQUARINGS
     with pytest.raises(_lib.RGError) as ei:
-        rg.calculate_fidelity_and_derivatives(fp, np.zeros(3))
+        rg.calculate_fidelity_and_derivatives(fp, np.zeros(2))
     assert ei.value.code == _lib.RG_ERR_NORM
 
 
@@ -236,3 +251,56 @@ def test_response_at_zero_frequency_matches_sensitivity(gpu_ctx):
     Rf, _ = rg.calculate_fidelity_response_fft(fp, x, oversampling=2)
     assert np.allclose(-s, 2 * R[0], rtol=1e-3, atol=1e-3)
     assert np.allclose(-s, 2 * Rf[0], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", ["cz5_e2", "cz7_e1", "detuned", "cz5_e0", "squared"])
+def test_unitary_and_derivatives_materialised(gpu_ctx, case):
+    """calculate_unitary_and_derivatives (reference src/UnitaryCalculations.jl:20-155): all six returned tensors.
+    U is well conditioned (1e-12); the derivative tensors are compared with the FP64 restatement at its
+    finite-difference noise floor (2e-5 / 2e-4 of the largest element) and, where cheap, with the exact-semantics
+    oracle at 1e-10."""
+    from oracle import exact_oracle as eo
+    if case == "cz5_e2":
+        fp = cz_problem(37, 7.613 * 37 / 300, ("amp", "freq")); p = 1
+    elif case == "cz7_e1":
+        fp = cz_problem(21, 1.5, ("amp",), "full_blockaded"); p = 1
+    elif case == "detuned":
+        fp = detuned_problem(13, 1.7, ("amp", "freq")); p = 2
+    elif case == "squared":
+        fp = cz_problem(4, 30.0, ("amp",)); p = 1
+    else:
+        fp = cz_problem(50, 2.0); p = 1
+    up = fp.unitary_problem
+    x = random_pulse(fp, p, 77)
+    got = rg.calculate_unitary_and_derivatives(up, x)
+    ref = ro.calculate_unitary_and_derivatives(up, x)
+    names = ["U", "U_dx", "U_dx_add", "U_derr", "U_derr_dx", "U_derr_dx_add"]
+    tol = {"U": 1e-12, "U_dx": 2e-5, "U_dx_add": 2e-5, "U_derr": 2e-5, "U_derr_dx": 2e-4, "U_derr_dx_add": 2e-4}
+    for n, g, r in zip(names, got, ref):
+        assert g.shape == r.shape, n
+        if r.size and np.abs(r).max() > 0:
+            assert np.abs(g - r).max() <= tol[n] * np.abs(r).max(), (n, np.abs(g - r).max() / np.abs(r).max())
+        else:
+            assert np.abs(g).max() == 0 if g.size else True
+    # exact-semantics check of every tensor
+    ex = eo.calculate_unitary_and_derivatives(up, x)
+    d, N, a, e = up.ndim, up.ntimes, up.nb_additional_param, len(up.error_sources)
+    tom = lambda M: np.array([[complex(M[i, j]) for j in range(d)] for i in range(d)])
+    tol_ex = 1e-9 if case == "squared" else 1e-10
+    assert np.abs(got[0] - tom(ex[0])).max() < 1e-13 * (30 if case == "squared" else 1)
+    for i in range(p):
+        for k in range(0, N, max(1, N // 5)):
+            r = tom(ex[1][i][k])
+            assert np.abs(got[1][:, :, i, k] - r).max() <= tol_ex * max(np.abs(r).max(), 1e-300)
+            for ee in range(e):
+                r = tom(ex[4][i][k][ee])
+                assert np.abs(got[4][:, :, i, k, ee] - r).max() <= tol_ex * np.abs(r).max()
+    for ee in range(e):
+        r = tom(ex[3][ee])
+        assert np.abs(got[3][:, :, ee] - r).max() <= tol_ex * np.abs(r).max()
+        for j in range(a):
+            r = tom(ex[5][j][ee])
+            assert np.abs(got[5][:, :, j, ee] - r).max() <= tol_ex * max(np.abs(r).max(), 1e-30) + 1e-300
+    for j in range(a):
+        r = tom(ex[2][j])
+        assert np.abs(got[2][:, :, j] - r).max() <= tol_ex * max(np.abs(r).max(), 1e-30) + 1e-300
