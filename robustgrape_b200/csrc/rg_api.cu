@@ -515,7 +515,16 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
                                                        pr->Wlb.as<cplx>(), ctx->d_status);
     }
     // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
-    if (ne > 0 && want_grad && P.nvar > 0) {
+    if (ne > 0 && want_grad && P.nvar > 0 && fast && PID != PAT_FULL) {
+        // structured fast path: thread per step, four triangles in registers
+        constexpr int DT = kThreadOK ? D : 2;
+        constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
+        const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
+        const long long items = (long long)B * P.N;
+        KTimer kt(ctx, RG_K_STEPS_SO);
+        if constexpr (PID != PAT_FULL)
+            k_steps_so_t<DT, UM><<<(int)((items + 127) / 128), 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+    } else if (ne > 0 && want_grad && P.nvar > 0) {
         const int gs = k1b_group_stride(D, P.nterms);
         const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
         int wpc = 4;

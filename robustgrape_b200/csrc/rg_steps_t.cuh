@@ -205,6 +205,176 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     }
 }
 
+
+// ------------------------------------------------------------------ mixed second differences, thread per step
+// t += M v for a skew-Hermitian M given by its upper triangle; column l of the closure pattern decides which
+// components of v can be non-zero.  mrt: run-time (warp-uniform) mask of M within the compile-time UMASK.
+template <int D, unsigned UMASK, int l>
+__device__ __forceinline__ void tri_matvec_acc(cplx (&t)[D], const cplx (&tri)[Tri<D>::n], unsigned mrt, const cplx (&v)[D]) {
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    constexpr bool MASKED = (UMASK != ((1u << Tri<D>::n) - 1u));
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+            const int pos = Tri<D>::idx(i, k);
+            if (!((UMASK >> pos) & 1u)) continue;
+            if (!PT::has(k, l) && !PT::has(i, l)) continue;
+            if (MASKED && !((mrt >> pos) & 1u)) continue;
+            const cplx a = tri[pos];
+            if (PT::has(k, l)) cfma(t[i], a, v[k]);
+            if (i != k && PT::has(i, l)) cfma_nconj(t[k], a, v[i]);
+        }
+}
+// column l of a skew-Hermitian matrix given by its triangle, scaled
+template <int D, unsigned UMASK, int l>
+__device__ __forceinline__ void tri_column(cplx (&y)[D], const cplx (&tri)[Tri<D>::n], double sc) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = cmk(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i <= k; ++i) {
+            if (!((UMASK >> Tri<D>::idx(i, k)) & 1u)) continue;
+            const cplx a = tri[Tri<D>::idx(i, k)];
+            if (k == l) y[i] = cscale(a, sc);
+            if (i == l && i != k) y[k] = cscale(cmk(-a.x, a.y), sc);
+        }
+}
+
+template <int D, unsigned UMASK, int l>
+__device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cplx (&tal)[Tri<D>::n], const cplx (&tbe)[Tri<D>::n],
+                                           const cplx (&tga)[Tri<D>::n], unsigned mA, unsigned mAl, unsigned mBe, int m,
+                                           bool live, cplx* __restrict__ dst) {
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    if constexpr (l < D) {
+        cplx y[D], da[D], db[D], dab[D];
+        const double inv0 = c_inv_j[m];
+        tri_column<D, UMASK, l>(y, ta, inv0);
+        y[l].x += 1.0;
+        tri_column<D, UMASK, l>(da, tal, inv0);
+        tri_column<D, UMASK, l>(db, tbe, inv0);
+        tri_column<D, UMASK, l>(dab, tga, inv0);
+        for (int j = m - 1; j >= 1; --j) {
+            const double inv = c_inv_j[j];
+            cplx acc[D], s[D];
+            // dab' = (A dab + al (db + dab) + be (da + dab) + ga (y + da + db + dab)) / j
+#pragma unroll
+            for (int i = 0; i < D; ++i) acc[i] = cmk(0.0, 0.0);
+            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, dab);
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = cadd(db[i], dab[i]);
+            tri_matvec_acc<D, UMASK, l>(acc, tal, mAl, s);
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = cadd(da[i], dab[i]);
+            tri_matvec_acc<D, UMASK, l>(acc, tbe, mBe, s);
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = cadd(cadd(y[i], da[i]), cadd(db[i], dab[i]));
+            tri_matvec_acc<D, UMASK, l>(acc, tga, mBe, s);
+#pragma unroll
+            for (int i = 0; i < D; ++i) dab[i] = cscale(acc[i], inv);
+            // da' = (A da + al (y + da)) / j
+#pragma unroll
+            for (int i = 0; i < D; ++i) { acc[i] = cmk(0.0, 0.0); s[i] = cadd(y[i], da[i]); }
+            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, da);
+            tri_matvec_acc<D, UMASK, l>(acc, tal, mAl, s);
+#pragma unroll
+            for (int i = 0; i < D; ++i) da[i] = cscale(acc[i], inv);
+            // db' = (A db + be (y + db)) / j
+#pragma unroll
+            for (int i = 0; i < D; ++i) { acc[i] = cmk(0.0, 0.0); s[i] = cadd(y[i], db[i]); }
+            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, db);
+            tri_matvec_acc<D, UMASK, l>(acc, tbe, mBe, s);
+#pragma unroll
+            for (int i = 0; i < D; ++i) db[i] = cscale(acc[i], inv);
+            // y' = I + A y / j
+#pragma unroll
+            for (int i = 0; i < D; ++i) acc[i] = cmk(0.0, 0.0);
+            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, y);
+#pragma unroll
+            for (int i = 0; i < D; ++i) y[i] = cscale(acc[i], inv);
+            y[l].x += 1.0;
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (PT::has(i, l)) dst[PT::idx(i, l)] = dab[i];
+        }
+        so_columns<D, UMASK, l + 1>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
+    }
+}
+
+// One thread per time step: mixed second differences d2U^{v,e} at (eps2, eps2) for every (variable, error source).
+// Only instantiated for structural masks small enough to keep four triangles in registers.
+template <int D, unsigned UMASK>
+__global__ void __launch_bounds__(128, 2)
+k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
+             int* __restrict__ status) {
+    constexpr int NP = Tri<D>::n;
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    extern __shared__ cplx smem[];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    const long long total = (long long)B * P.N;
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = item < total;
+    if (!live) item = total - 1;
+    const int b = (int)(item / P.N), k = (int)(item % P.N);
+    const double* xp = X + (size_t)b * P.nx;
+    double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
+    for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
+    for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * PT::nnz;
+    const int nt = P.nterms, nv = P.nvar, ne = P.e;
+
+    cplx cA[RG_T_MAX_TERMS], cB[RG_T_MAX_TERMS], cC[RG_T_MAX_TERMS];
+    cplx ta[NP], tal[NP], tbe[NP], tga[NP];
+    int m = 0;
+    for (int e = 0; e < ne; ++e)
+        for (int v = 0; v < nv; ++v) {
+            const int sp_ = P.var_space[v], ix = P.var_index[v];
+            const double val = (sp_ == RG_S_MAIN) ? xk[ix] : xadd[ix];
+            const double h2 = __dsub_rn(__dadd_rn(val, P.eps2), val);
+            EvalCtx ec{xk, xadd, P.eps2, P.table, P.N, k};
+            for (int t = 0; t < nt; ++t) {
+                cplx base = cmk(0, 0), del = cmk(0, 0);
+                const DevTerm& tm = sp.terms[t];
+                const bool isH0 = tm.owner == RG_OWNER_H0;
+                if (sp.used[t] && (isH0 || tm.owner == e)) term_coef(tm, ec, sp_, ix, h2, base, del);
+                const cplx sb = cmk(base.y * P.dt, -base.x * P.dt), sd2 = cmk(del.y * P.dt, -del.x * P.dt);
+                cA[t] = isH0 ? sb : cmk(0, 0);        // A      : H0 value
+                cB[t] = isH0 ? sd2 : sb;              // alpha  : H0 difference in v   | beta : error value at eps2
+                cC[t] = isH0 ? cmk(0, 0) : sd2;       // gamma  : error difference in v at eps2
+            }
+#pragma unroll
+            for (int pos = 0; pos < NP; ++pos) {
+                if (!((UMASK >> pos) & 1u)) continue;
+                cplx a = cmk(0, 0), al = cmk(0, 0), be = cmk(0, 0), ga = cmk(0, 0);
+                for (int q = sp.ptr[pos]; q < sp.ptr[pos + 1]; ++q) {
+                    const int t = sp.term[q];
+                    const cplx vv = sp.val[q];
+                    const bool isH0 = sp.terms[t].owner == RG_OWNER_H0;
+                    cfma(a, cA[t], vv);
+                    if (isH0) cfma(al, cB[t], vv); else cfma(be, cB[t], vv);
+                    cfma(ga, cC[t], vv);
+                }
+                ta[pos] = a; tal[pos] = al; tbe[pos] = be; tga[pos] = ga;
+            }
+            if (e == 0 && v == 0) {
+                double nrm = 0.0;
+                for (int kk = 0; kk < D; ++kk) {
+                    double s = 0.0;
+                    for (int t = 0; t < nt; ++t) { const cplx c = cA[t]; s += sqrt(c.x * c.x + c.y * c.y) * sp.colw[t * D + kk]; }
+                    nrm = fmax(nrm, s);
+                }
+                m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
+                m = __reduce_max_sync(0xffffffffu, m);
+                if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 2); m = 18; }
+            }
+            so_columns<D, UMASK, 0>(ta, tal, tbe, tga, tp.maskA, tp.maskVar[v], tp.maskErr[e], m, live,
+                                    wsk + (size_t)(1 + nv + ne + e * nv + v) * PT::nnz);
+        }
+}
+
 // Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
 template <int D, u64 CM>
 __global__ void __launch_bounds__(128)
