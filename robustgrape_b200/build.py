@@ -9,8 +9,10 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "librobustgrape_b200.so"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-diag-suppress", "68,20058", "-shared", "-Xcompiler", "-fPIC"]
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                 "-diag-suppress", "68,20058", "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
+OBJ_DIR = ROOT / "lib" / "obj"
 
 
 def _nvcc():
@@ -33,13 +35,30 @@ def needs_build():
 
 
 def build_cuda(force=False, verbose=False):
+    """Compile every csrc/*.cu for sm_100a (one nvcc process per translation unit, in parallel) and link the
+    in-tree shared library."""
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in sources():
+        obj = OBJ_DIR / (src.stem + ".o")
+        cmd = [nvcc, *COMPILE_FLAGS, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            for _, _, q in procs:
+                if q.poll() is None:
+                    q.kill()
+            raise RuntimeError(f"nvcc failed on {src.name}:\n{out}")
+        objs.append(str(obj))
+    r = subprocess.run([nvcc, *LINK_FLAGS, "-o", str(LIB), *objs], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB

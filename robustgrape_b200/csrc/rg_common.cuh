@@ -163,7 +163,7 @@ __device__ __forceinline__ void expm_plan(double nrm, int& m, int& s) {
 // (block-diagonal for the Rydberg models).  CM has bit (i + D*j) set for every element that can be
 // non-zero; only those are stored in the HBM workspace, loaded and multiplied.
 typedef unsigned long long u64;
-template <int D> __host__ __device__ constexpr u64 full_cmask() { return (D * D >= 64) ? ~0ull : ((1ull << (D * D)) - 1ull); }
+template <int D> __host__ __device__ constexpr u64 full_cmask() { return ~0ull; }   // all-ones = dense pattern, any d
 __host__ __device__ constexpr int cx_popc(u64 v) { int c = 0; while (v) { v &= v - 1; ++c; } return c; }
 // closure of an upper-triangle mask (bit k(k+1)/2 + i, i <= k) as a full d x d pattern
 __host__ __device__ constexpr u64 closure_from_tri(int d, unsigned tri) {
@@ -185,9 +185,10 @@ __host__ __device__ constexpr u64 closure_from_tri(int d, unsigned tri) {
 template <int D, u64 CM> struct Pat {
     static constexpr int nnz = cx_popc(CM);
     static constexpr bool full = (CM == full_cmask<D>());
-    __host__ __device__ static constexpr bool has(int i, int j) { return (CM >> (i + D * j)) & 1ull; }
-    __host__ __device__ static constexpr int idx(int i, int j) { return full ? (i + D * j) : cx_popc(CM & ((1ull << (i + D * j)) - 1ull)); }
+    // patterns are only representable for d*d <= 64; larger d always use the full (dense) pattern
+    __host__ __device__ static constexpr bool has(int i, int j) { return full || ((i + D * j) < 64 && ((CM >> ((i + D * j) & 63)) & 1ull)); }
+    __host__ __device__ static constexpr int idx(int i, int j) { return full ? (i + D * j) : cx_popc(CM & ((1ull << ((i + D * j) & 63)) - 1ull)); }
 };
 // run-time versions (warp-uniform mask from DevProblem)
-__device__ __forceinline__ bool pat_has(u64 cm, int d, int i, int j) { return (cm >> (i + d * j)) & 1ull; }
-__device__ __forceinline__ int pat_idx(u64 cm, int d, int i, int j) { return __popcll(cm & ((1ull << (i + d * j)) - 1ull)); }
+__device__ __forceinline__ bool pat_has(u64 cm, int d, int i, int j) { return cm == ~0ull || ((cm >> ((i + d * j) & 63)) & 1ull); }
+__device__ __forceinline__ int pat_idx(u64 cm, int d, int i, int j) { return cm == ~0ull ? (i + d * j) : __popcll(cm & ((1ull << ((i + d * j) & 63)) - 1ull)); }

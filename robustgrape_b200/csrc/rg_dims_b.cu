@@ -1,0 +1,3 @@
+// Instantiates the kernels and launch templates for ndim = 5 (see rg_host.cuh).
+#include "rg_host.cuh"
+RG_DEFINE_DIM(5)

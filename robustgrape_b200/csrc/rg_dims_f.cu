@@ -1,0 +1,3 @@
+// Instantiates the kernels and launch templates for ndim = 16 (see rg_host.cuh).
+#include "rg_host.cuh"
+RG_DEFINE_DIM(16)

@@ -1,0 +1,447 @@
+// rg_host.cuh -- host-side structs and the per-dimension launch templates.  Every rg_dims_*.cu translation
+// unit instantiates these for a few Hilbert-space dimensions (compiled in parallel); rg_api.cu holds the C ABI.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+enum { RG_K_STEPS = 0, RG_K_STEPS_SO = 1, RG_K_SCAN = 2, RG_K_GRAD = 3, RG_K_GRAD_ERR = 4, RG_K_EPILOGUE = 5, RG_K_ANALYSIS = 6, RG_K_AGG = 7, RG_NKERNELS = 8 };
+#include "rg_smalld.cuh"
+#include "rg_steps_t.cuh"
+#include "rg_analysis.cuh"
+
+struct rg_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int* d_status = nullptr;
+    int* h_status = nullptr;    // pinned
+    int sm_count = 148;
+    size_t ws_limit = (size_t)64 << 30;
+    // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
+    int host_slabs = 4;                               // RG_HOST_SLABS (upper bound; slabs hold >= 2048 pulses)
+    bool timing = false;
+    struct Span { int kernel; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
+    double kern_ms[RG_NKERNELS] = {0};
+    int64_t kern_n[RG_NKERNELS] = {0};
+};
+
+struct KTimer {
+    rg_ctx* c; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KTimer(rg_ctx* c_, int k_) : c(c_), k(k_) {
+        if (c->timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    }
+    ~KTimer() {
+        c->launches++;
+        if (c->timing) { cudaEventRecord(e1, c->stream); c->spans.push_back({k, e0, e1}); }
+    }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct rg_problem {
+    rg_ctx* ctx = nullptr;
+    DevProblem dp{};
+    std::vector<void*> owned;          // device allocations of the descriptor
+    int any_add_dep = 0;
+    int chunk_override = 0;
+    int force_dense = 0;      // RG_DENSE=1: treat H as dense (no structural-zero skipping)
+    int force_group = 0;      // RG_GROUP=1: force the group-per-chunk k_steps kernel
+    TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
+    int tri_ok = 0;
+    double tri_density = 1.0;
+    unsigned tri_union = 0;   // union of all structural masks
+    // workspaces
+    DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2, dO, dFreq, dM;
+    int has_target = 0;
+};
+
+#define RG_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        char _b[512];                                             \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                    \
+        (ctx)->err = _b;                                          \
+        return (code);                                            \
+    } while (0)
+
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            RG_FAIL(ctx, RG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                      \
+    } while (0)
+
+
+// ---- per-dimension operations table (defined by RG_DEFINE_DIM in rg_dims_*.cu) --------------------------
+struct Plan;
+struct DimOps {
+    int (*run_slab)(rg_problem*, int, const Plan&, const double*, int, const double*, double*, double*, double*, double*, bool);
+    int (*materialize)(rg_problem*, const double*, cplx*, cplx*, cplx*, cplx*, cplx*, cplx*);
+    int (*interaction)(rg_problem*, const double*, cplx*);
+    int (*response)(rg_problem*, const double*, int, int, int, int, double*);
+    int (*expectation)(rg_problem*, double*);
+};
+const DimOps* rg_dim_ops(int d);
+
+// ------------------------------------------------------------------------------------------
+struct Plan { int L, nc, slab; };
+
+static inline Plan make_plan(const rg_problem* pr, int B) {
+    const DevProblem& P = pr->dp;
+    Plan pl;
+    const size_t per_pulse = (size_t)P.N * P.nstore * P.d * P.d * sizeof(cplx);
+    size_t slab = std::max<size_t>(1, pr->ctx->ws_limit / std::max<size_t>(per_pulse, 1));
+    pl.slab = (int)std::min<size_t>(slab, (size_t)B);
+    // enough (pulse, chunk) work items for ~8 waves of resident groups
+    const long long target_items = (long long)pr->ctx->sm_count * 72 * 8;
+    long long want_nc = (target_items + pl.slab - 1) / pl.slab;
+    // chunk length: long enough that the per-pulse sequential chunk scan (k_scan, latency bound) stays short,
+    // short enough to expose (pulse, chunk) parallelism for small batches
+    const long long lmin = (pl.slab >= 64) ? 16 : 4;
+    int L = (int)std::max<long long>(lmin, std::min<long long>(32, P.N / std::max<long long>(1, want_nc)));
+    if (pr->chunk_override > 0) L = pr->chunk_override;
+    L = std::min(L, P.N);
+    pl.L = L;
+    pl.nc = (P.N + L - 1) / L;
+    return pl;
+}
+
+template <class K>
+static int set_smem(rg_ctx* ctx, K kern, size_t bytes) {
+    if (bytes > 227 * 1024) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory", bytes);
+    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return RG_OK;
+}
+
+// Structural patterns instantiated ahead of time (upper-triangle bit = k(k+1)/2 + i, i <= k).  A problem
+// whose union mask fits one of them gets kernels with the zero positions removed at compile time; anything
+// else runs the full (dense) instantiation.  (Arbitrary patterns: NVRTC specialisation, see DESIGN.md.)
+//   PAT_M5_DRIVE: 5-level symmetric-blockaded Rydberg model (src/RydbergTools.jl:31-39), drive only: (1,3),(2,4)
+//   PAT_M5_FULL : same plus the Rydberg detuning diagonal (3,3),(4,4) (frequency error / delta != 0)
+enum { PAT_FULL = 0, PAT_M5_DRIVE = 1, PAT_M5_FULL = 2 };
+template <int D, int PID> constexpr unsigned tri_mask_of() {
+    return (D == 5 && PID == PAT_M5_DRIVE) ? ((1u << 7) | (1u << 12))
+         : (D == 5 && PID == PAT_M5_FULL) ? ((1u << 7) | (1u << 12) | (1u << 9) | (1u << 14))
+         : ((D * (D + 1) / 2 >= 32) ? ~0u : ((1u << (D * (D + 1) / 2)) - 1u));
+}
+template <int D, int PID> constexpr u64 cmask_of() {
+    return (PID == PAT_FULL) ? full_cmask<D>() : closure_from_tri(D, tri_mask_of<D, PID>());
+}
+
+// Run the fused path for one slab of pulses already resident on the device.
+//   mode 0: fidelity + derivatives  -> dF, dFdx (+1 scale), dF2, dF2dx
+//   mode 1: cost + grad             -> dcost (in dF slot), dgrad (in dFdx slot)
+template <int D, int PID>
+static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mode, const double* d_coeff,
+                    double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
+    rg_ctx* ctx = pr->ctx;
+    constexpr u64 CM = cmask_of<D, PID>();
+    constexpr int WSM = Pat<D, CM>::nnz;
+    DevProblem P = pr->dp;
+    P.wsm = WSM; P.cmask = CM;
+    constexpr int G = GroupInfo<D>::G;
+    const int DD = D * D, ne = P.e, nc = pl.nc, L = pl.L;
+    cudaStream_t st = ctx->stream;
+    if (!pr->has_target) RG_FAIL(ctx, RG_ERR_INVALID, "problem has no target/projector: fidelity entry points unavailable");
+    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported by the fused path yet");
+
+    const size_t cb = sizeof(cplx);
+    if (pr->ws.ensure((size_t)B * P.N * P.nstore * WSM * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
+        pr->Wlb.ensure(std::max<size_t>(16, (size_t)B * nc * ne * DD * cb)) || pr->Cb.ensure((size_t)B * nc * DD * cb) ||
+        pr->Wb.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) || pr->Gb.ensure((size_t)B * nc * DD * cb) ||
+        pr->G1b.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) ||
+        pr->H1b.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) ||
+        pr->F.ensure((size_t)B * 8) || pr->F2.ensure(std::max<size_t>(16, (size_t)B * ne * 8)) ||
+        pr->addT.ensure(std::max<size_t>(16, (size_t)B * (1 + ne) * P.a * 8)) ||
+        pr->addS.ensure(std::max<size_t>(16, pr->any_add_dep ? (size_t)B * (1 + ne) * P.a * P.N * 8 : 16)))
+        RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed (B=%d)", B);
+    double* iF = dF ? dF : pr->F.as<double>();
+    double* iF2 = dF2 ? dF2 : pr->F2.as<double>();
+    if (mode == 1) { iF = pr->F.as<double>(); iF2 = pr->F2.as<double>(); }
+    double* iF2dx = dF2dx;
+    if (want_grad && ne > 0 && (mode == 1 || !dF2dx)) {
+        if (pr->F2dx.ensure((size_t)B * ne * P.nx * 8)) RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed");
+        iF2dx = pr->F2dx.as<double>();
+    }
+    double* iFdx = dFdx;
+    if (want_grad && !iFdx) {
+        if (pr->Fdx.ensure((size_t)B * P.nx * 8)) RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed");
+        iFdx = pr->Fdx.as<double>();
+    }
+
+    // ---- K1: step propagators + first-order differences (+ chunk aggregates)
+    constexpr bool kThreadOK = (D <= 5);
+    const bool fast = kThreadOK && pr->tri_ok && !pr->force_group;
+    if (!fast && PID != PAT_FULL) RG_FAIL(ctx, RG_ERR_INVALID, "internal: structural pattern without the fast path");
+    if (fast) {
+        // Hermitian fast path: one thread per time step, triangles in registers; aggregates in a second kernel.
+        constexpr int DT = kThreadOK ? D : 2;
+        constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
+        const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
+        const long long items = (long long)B * P.N;
+        const int grid = (int)((items + 127) / 128);
+        {
+            KTimer kt(ctx, RG_K_STEPS);
+            k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+        }
+        const int gs = kagg_group_stride(D, ne);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+        const size_t smem2 = (size_t)wpc * G * gs * cb;
+        int rc = set_smem(ctx, k_chunk_agg<D, CM>, smem2);
+        if (rc) return rc;
+        const long long citems = (long long)B * nc;
+        const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_AGG);
+        k_chunk_agg<D, CM><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+    } else {
+        const int gs = k1_group_stride(D, P.nterms, ne);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps<D, false>, smem);
+        if (rc) return rc;
+        const long long items = (long long)B * nc;
+        const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_STEPS);
+        k_steps<D, false><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+                                                       pr->Wlb.as<cplx>(), ctx->d_status);
+    }
+    // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
+    if (ne > 0 && want_grad && P.nvar > 0 && fast && PID != PAT_FULL) {
+        // structured fast path: thread per step, four triangles in registers
+        constexpr int DT = kThreadOK ? D : 2;
+        constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
+        const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
+        const long long items = (long long)B * P.N;
+        KTimer kt(ctx, RG_K_STEPS_SO);
+        if constexpr (PID != PAT_FULL)
+            k_steps_so_t<DT, UM><<<(int)((items + 127) / 128), 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+    } else if (ne > 0 && want_grad && P.nvar > 0) {
+        const int gs = k1b_group_stride(D, P.nterms);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps_so<D>, smem);
+        if (rc) return rc;
+        const long long items = (long long)B * P.N;
+        const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
+        KTimer kt(ctx, RG_K_STEPS_SO);
+        k_steps_so<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+    }
+    // ---- K2
+    {
+        const int gs = k2_group_stride(D);
+        int wpc = 2;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb;
+        int rc = set_smem(ctx, k_scan<D>, smem);
+        if (rc) return rc;
+        dim3 grid((B + wpc * G - 1) / (wpc * G), 1 + ne);
+        KTimer kt(ctx, RG_K_SCAN);
+        k_scan<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, nc, pr->Qb.as<cplx>(), pr->Wlb.as<cplx>(), pr->Cb.as<cplx>(),
+                                               pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(),
+                                               iF, iF2, pr->addT.as<double>(), 0, nullptr, nullptr);
+    }
+    const double DD1 = P.Dtr * (P.Dtr + 1.0);
+    // mode 1 with no error sources writes -F_dx straight into grad
+    const double sign0 = (mode == 1 && ne == 0) ? -1.0 : 1.0;
+    if (want_grad) {
+        // ---- K3: backward gradient sweeps (fidelity role, then one role per error source)
+        const long long items = (long long)B * nc;
+        {
+            const int gs = k3_group_stride(D, 1 + P.nvar);
+            int wpc = 4;
+            while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+            const size_t smem = (size_t)wpc * G * gs * cb;
+            int rc = set_smem(ctx, k_grad<D, false, CM>, smem);
+            if (rc) return rc;
+            dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), 1);
+            KTimer kt(ctx, RG_K_GRAD);
+            k_grad<D, false, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+                pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
+                sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
+        }
+        if (ne > 0) {
+            const int gs = k3_group_stride(D, 2 + 2 * P.nvar);
+            int wpc = 4;
+            while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+            const size_t smem = (size_t)wpc * G * gs * cb;
+            int rc = set_smem(ctx, k_grad<D, true, CM>, smem);
+            if (rc) return rc;
+            dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), ne);
+            KTimer kt(ctx, RG_K_GRAD_ERR);
+            k_grad<D, true, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+                pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
+                0.0, iF2dx, pr->addS.as<double>());
+        }
+        // ---- K4: additional parameters
+        if (P.a > 0) {
+            const int n = B * (1 + ne) * P.a;
+            KTimer kt(ctx, RG_K_EPILOGUE);
+            k_add_params<<<(n + 127) / 128, 128, 0, st>>>(P, B, pr->addT.as<double>(), pr->addS.as<double>(), iFdx, sign0, iF2dx);
+        }
+    }
+    if (mode == 1) {
+        KTimer kt(ctx, RG_K_EPILOGUE);
+        if (ne > 0 && want_grad) {
+            const size_t n = (size_t)B * P.nx;
+            const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+            k_cost_grad<<<grid, 256, 0, st>>>(B, P.nx, ne, iF, iF2, iF2dx, d_coeff, dF, iFdx);
+        } else if (ne > 0) {
+            RG_FAIL(ctx, RG_ERR_INVALID, "cost without gradient is not exposed");
+        } else {
+            k_cost_only<<<(B + 255) / 256, 256, 0, st>>>(B, iF, dF);
+        }
+    }
+    CU(ctx, cudaGetLastError());
+    return RG_OK;
+}
+
+// Per-dimension entry: picks the structural pattern instantiation for this problem.
+template <int D>
+static int dim_run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mode, const double* d_coeff,
+                        double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
+    const bool fast = pr->tri_ok && !pr->force_group && !pr->force_dense;
+    if constexpr (D == 5) {
+        if (fast) {
+            if ((pr->tri_union & ~tri_mask_of<5, PAT_M5_DRIVE>()) == 0)
+                return run_slab<5, PAT_M5_DRIVE>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+            if ((pr->tri_union & ~tri_mask_of<5, PAT_M5_FULL>()) == 0)
+                return run_slab<5, PAT_M5_FULL>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+        }
+    }
+    return run_slab<D, PAT_FULL>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
+}
+
+// ---- calculate_unitary_and_derivatives, materialised (one pulse) ---------------------------------------
+template <int D>
+static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU_dx, cplx* dU_dx_add, cplx* dU_derr,
+                            cplx* dU_derr_dx, cplx* dU_derr_dx_add) {
+    rg_ctx* ctx = pr->ctx;
+    constexpr u64 CM = full_cmask<D>();
+    DevProblem P = pr->dp;
+    P.wsm = D * D; P.cmask = CM;
+    constexpr int G = GroupInfo<D>::G;
+    const int DD = D * D, ne = P.e;
+    const size_t cb = sizeof(cplx);
+    cudaStream_t st = ctx->stream;
+    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported yet");
+    int L = std::max(1, std::min(16, P.N / 64));
+    if (pr->chunk_override > 0) L = std::min(pr->chunk_override, P.N);
+    const int nc = (P.N + L - 1) / L;
+    if (pr->ws.ensure((size_t)P.N * P.nstore * DD * cb) || pr->Qb.ensure((size_t)nc * DD * cb) ||
+        pr->Wlb.ensure(std::max<size_t>(16, (size_t)nc * ne * DD * cb)) || pr->Cb.ensure((size_t)nc * DD * cb) ||
+        pr->Wb.ensure(std::max<size_t>(16, (size_t)ne * nc * DD * cb)) || pr->Gb.ensure((size_t)nc * DD * cb) ||
+        pr->G1b.ensure(std::max<size_t>(16, (size_t)ne * nc * DD * cb)) || pr->H1b.ensure(std::max<size_t>(16, (size_t)ne * nc * DD * cb)) ||
+        pr->dM.ensure(std::max<size_t>(16, (size_t)(1 + ne) * P.a * P.N * DD * cb)))
+        RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed");
+    {   // general group kernel: propagators, first-order differences, chunk aggregates (with scaling-and-squaring)
+        const int gs = k1_group_stride(D, P.nterms, ne);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps<D, false>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_STEPS);
+        k_steps<D, false><<<(nc + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(P, dx, 1, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+                                                                                pr->Wlb.as<cplx>(), ctx->d_status);
+    }
+    if (ne > 0 && P.nvar > 0) {
+        const int gs = k1b_group_stride(D, P.nterms);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps_so<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_STEPS_SO);
+        k_steps_so<D><<<(P.N + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(P, dx, 1, pr->ws.as<cplx>(), ctx->d_status);
+    }
+    {
+        const int gs = k2_group_stride(D);
+        const size_t smem = (size_t)G * gs * cb;
+        int rc = set_smem(ctx, k_scan<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_SCAN);
+        k_scan<D><<<dim3(1, 1 + ne), 32, smem, st>>>(P, dx, 1, nc, pr->Qb.as<cplx>(), pr->Wlb.as<cplx>(), pr->Cb.as<cplx>(),
+                                                   pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(),
+                                                   nullptr, nullptr, nullptr, 1, dU, dU_derr);
+    }
+    {
+        const int nload_max = (ne > 0) ? (2 + 2 * P.nvar) : (1 + P.nvar);
+        const int gs = kmat_group_stride(D, nload_max);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb;
+        int rc = set_smem(ctx, k_materialize<D, CM>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_ANALYSIS);
+        k_materialize<D, CM><<<dim3((nc + wpc * G - 1) / (wpc * G), 1 + ne), wpc * 32, smem, st>>>(
+            P, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(), pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(),
+            pr->H1b.as<cplx>(), dU_dx, dU_derr_dx, pr->dM.as<cplx>());
+    }
+    if (P.a > 0) {
+        const int n = (1 + ne) * P.a * DD;
+        KTimer kt(ctx, RG_K_ANALYSIS);
+        k_reduce_add<<<(n + 127) / 128, 128, 0, st>>>(P, pr->dM.as<cplx>(), dU_dx_add, dU_derr_dx_add);
+    }
+    CU(ctx, cudaGetLastError());
+    return RG_OK;
+}
+
+// ---- interaction-picture error operators on the device (shared by the three analysis entry points)
+template <int D>
+static int launch_interaction(rg_problem* pr, const double* dx, cplx* dO) {
+    rg_ctx* ctx = pr->ctx;
+    const DevProblem& P = pr->dp;
+    const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(5 * D * D + 2 * P.nterms) * sizeof(cplx);
+    int rc = set_smem(ctx, k_interaction_ops<D>, smem);
+    if (rc) return rc;
+    KTimer kt(ctx, RG_K_ANALYSIS);
+    k_interaction_ops<D><<<1, 32, smem, ctx->stream>>>(P, dx, dO, ctx->d_status);
+    return RG_OK;
+}
+template <int D>
+static int launch_response(rg_problem* pr, const double* dfreqs, int first, int count, int M, int shift, double* dR) {
+    rg_ctx* ctx = pr->ctx;
+    KTimer kt(ctx, RG_K_ANALYSIS);
+    dim3 grid(count, pr->dp.e);
+    k_response<D><<<grid, 128, 0, ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dfreqs, first, count, M, shift, dR);
+    return RG_OK;
+}
+template <int D>
+static int launch_expectation(rg_problem* pr, double* dOut) {
+    KTimer kt(pr->ctx, RG_K_ANALYSIS);
+    k_expectation<D><<<pr->dp.e, 32, 0, pr->ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dOut);
+    return RG_OK;
+}
+
+#define RG_DEFINE_DIM(D)                                                                                         \
+    extern const DimOps rg_ops_d##D = {dim_run_slab<D>, materialize_impl<D>, launch_interaction<D>, launch_response<D>, \
+                                       launch_expectation<D>};

@@ -4,7 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double a, double b) {
+static __global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double a, double b) {
     double r[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = threadIdx.x * 1e-3 + i;
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, doubl
     if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(256) k_peak_dmma(double* out, int iters, double a, double b) {
+static __global__ void __launch_bounds__(256) k_peak_dmma(double* out, int iters, double a, double b) {
     double c[8][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-3; c[i][1] = i; }

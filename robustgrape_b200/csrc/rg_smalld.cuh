@@ -21,7 +21,10 @@
 #pragma once
 #include "rg_common.cuh"
 
-__constant__ double c_inv_j[32];   // 1/j for the Horner recurrences
+// 1/j for the Horner recurrences (statically initialised: every translation unit has its own copy)
+__constant__ double c_inv_j[32] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+                                   1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+                                   1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31};
 
 enum { VK_DX = 0, VK_ERR = 1, VK_ERR_DX = 2, VK_BASE = 3, VK_TGT = 4, VK_TGT_DX = 5 };
 enum { OPN = 0, OPC = 1, OPT = 2 };
@@ -1321,7 +1324,7 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
 }
 // U_dx_add[:,:,j] / U_derr_dx_add[:,:,j,e] = sum over time of the per-step matrices (src/UnitaryCalculations.jl:119-121,140-151);
 // exact zero for additional parameters the Hamiltonian does not depend on.
-__global__ void k_reduce_add(const DevProblem P, const cplx* __restrict__ addM, cplx* __restrict__ U_dx_add, cplx* __restrict__ U_derr_dx_add) {
+static __global__ void k_reduce_add(const DevProblem P, const cplx* __restrict__ addM, cplx* __restrict__ U_dx_add, cplx* __restrict__ U_derr_dx_add) {
     const int DD = P.d * P.d;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nrole = 1 + P.e;
@@ -1339,7 +1342,7 @@ __global__ void k_reduce_add(const DevProblem P, const cplx* __restrict__ addM, 
 // ======================================================================================
 // x_add gradient entries: target part (from K2) + sum over time of the H-dependence part (from K3).
 // role 0 part is scaled by scale0 (already applied to addS role 0 entries in K3; applied here to addT).
-__global__ void k_add_params(const DevProblem P, int B, const double* __restrict__ addT, const double* __restrict__ addS,
+static __global__ void k_add_params(const DevProblem P, int B, const double* __restrict__ addT, const double* __restrict__ addS,
                              double* __restrict__ out0, double scale0T, double* __restrict__ out1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nrole = 1 + P.e;
@@ -1358,7 +1361,7 @@ __global__ void k_add_params(const DevProblem P, int B, const double* __restrict
 
 // cost = 1 - F + sum_e c_e F2_e^2 ; grad = -F_dx + 2 sum_e c_e F2_e F2dx_e   (src/FidelityCalculations.jl:178-184)
 // grad holds F_dx on entry when ne > 0 (written by K3/K4 with scale +1).
-__global__ void k_cost_grad(int B, int nx, int ne, const double* __restrict__ F, const double* __restrict__ F2,
+static __global__ void k_cost_grad(int B, int nx, int ne, const double* __restrict__ F, const double* __restrict__ F2,
                             const double* __restrict__ F2dx, const double* __restrict__ coeff /* device, ne */,
                             double* __restrict__ cost, double* __restrict__ grad) {
     const size_t n = (size_t)B * nx;
@@ -1376,7 +1379,7 @@ __global__ void k_cost_grad(int B, int nx, int ne, const double* __restrict__ F,
         }
     }
 }
-__global__ void k_cost_only(int B, const double* __restrict__ F, double* __restrict__ cost) {
+static __global__ void k_cost_only(int B, const double* __restrict__ F, double* __restrict__ cost) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) cost[b] = 1.0 - F[b];
 }

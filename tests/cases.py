@@ -90,3 +90,52 @@ def golden_cases():
     fp = detuned_problem(9, 1.1, ("amp", "freq"))
     cases["detuned_p2_a2_e2_N9"] = (fp, random_pulse(fp, 2, 15))
     return cases
+
+
+def dense_random_problem(d, ntimes, nparam=2, nerr=1, seed=0, t0=None):
+    """BASELINE config 5 in miniature: H(k) = H_0 + sum_j x_j(k) H_j with GUE draws scaled to unit spectral norm,
+    Herr_e(err) = err * E_e, no additional parameters, projector = identity on the first min(d,4) levels,
+    constant Haar-random target on that block."""
+    from robustgrape_b200.descriptors import ConstantTarget
+    rng = np.random.default_rng(seed)
+
+    def gue():
+        g = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        h = (g + g.conj().T) / 2
+        return h / np.linalg.norm(h, 2)
+
+    def ent(M):
+        return tuple((r, c, M[r, c]) for r in range(d) for c in range(d))
+
+    terms = [Term(1.0, (), ent(gue()), OWNER_H0)]
+    for j in range(nparam):
+        terms.append(Term(1.0, (Factor.var(S_MAIN, j),), ent(gue()), OWNER_H0))
+    srcs = [rg.ErrorSource(TermErrorHamiltonian(d, [Term(1.0, (Factor.err(),), ent(gue()), e)])) for e in range(nerr)]
+    nb = min(d, 4)
+    proj = np.zeros((d, d)); proj[:nb, :nb] = np.eye(nb)
+    q, _ = np.linalg.qr(rng.normal(size=(nb, nb)) + 1j * rng.normal(size=(nb, nb)))
+    U0 = np.zeros((d, d), dtype=complex); U0[:nb, :nb] = q
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0 if t0 is not None else 0.05 * ntimes, ntimes=ntimes, ndim=d,
+                                      H0=TermHamiltonian(d, terms), nb_additional_param=0, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, proj, ConstantTarget(U0))
+
+
+def rydberg9_problem(ntimes, t0, errors=("amp",)):
+    """9-level two-atom model (reference src/RydbergTools.jl:118-130) with finite blockade and detunings."""
+    H0 = rt.rydberg_full_h0(1.0, 0.9, 0.05, -0.03, 8.0)
+    up_ent = ((1, 4, 0.5), (2, 5, 0.45), (3, 6, 0.5), (3, 7, 0.45), (6, 8, 0.45), (7, 8, 0.5))
+    dn_ent = tuple((c, r, v) for r, c, v in up_ent)
+    srcs = []
+    for i, e in enumerate(errors):
+        if e == "amp":
+            srcs.append(rg.ErrorSource(TermErrorHamiltonian(9, [
+                Term(1.0, (Factor.expi(S_MAIN, 0, -1.0), Factor.err1p_m1()), up_ent, i),
+                Term(1.0, (Factor.expi(S_MAIN, 0, +1.0), Factor.err1p_m1()), dn_ent, i)])))
+        else:
+            srcs.append(rg.ErrorSource(TermErrorHamiltonian(9, [Term(1.0, (Factor.err(),), tuple((r, r, 1.0) for r in range(4, 9)), i)])))
+    proj = np.diag([1.0, 1, 1, 1, 0, 0, 0, 0, 0])
+    tgt = TermTarget(9, [Term(1.0, (), ((0, 0, 1.0),), OWNER_TARGET),
+                         Term(1.0, (Factor.expi(S_ADD, 0, 1.0, 0.0),), ((1, 1, 1.0), (2, 2, 1.0)), OWNER_TARGET),
+                         Term(1.0, (Factor.expi(S_ADD, 0, 2.0, math.pi),), ((3, 3, 1.0),), OWNER_TARGET)])
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=9, H0=H0, nb_additional_param=1, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, proj, tgt)

@@ -308,3 +308,34 @@ def test_unitary_and_derivatives_materialised(gpu_ctx, case):
     for j in range(a):
         r = tom(ex[2][j])
         assert np.abs(got[2][:, :, j] - r).max() <= tol_ex * max(np.abs(r).max(), 1e-30) + 1e-300
+
+
+@pytest.mark.parametrize("d", [3, 6, 10, 12, 16])
+def test_dense_random_hamiltonians(gpu_ctx, d):
+    """Dense random-Hermitian control problems (BASELINE config 5 in miniature): p = 2 controls, one error source, no
+    additional parameters, identity-block projector, constant target.  d = 10, 12, 16 run the general (group) kernels."""
+    from cases import dense_random_problem
+    fp = dense_random_problem(d, 9, nparam=2, nerr=1, seed=d)
+    X = np.stack([np.random.default_rng(s).uniform(-1, 1, 18) for s in range(3)], axis=1)
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    for b in range(3):
+        a = ro.calculate_fidelity_and_derivatives(fp, X[:, b])
+        assert abs(F[b] - a[0]) < 1e-12
+        assert relmax(Fdx[:, b], a[1]) < 2e-5
+        assert relmax(F2[:, b], a[2]) < 2e-5
+        assert relmax(F2dx[:, :, b], a[3]) < 2e-4
+
+
+def test_nine_level_rydberg_model(gpu_ctx):
+    """reference src/RydbergTools.jl:118-130 (rydberg_hamiltonian_full) with cz_with_1q_phase_full, d = 9."""
+    from cases import rydberg9_problem
+    from oracle import exact_oracle as eo
+    fp = rydberg9_problem(7, 2.0, ("amp", "freq"))
+    x = random_pulse(fp, 1, 9)
+    got = rg.calculate_fidelity_and_derivatives(fp, x)
+    ex = eo.calculate_fidelity_and_derivatives(fp, x)
+    for k, g, e in zip(NAMES, got, ex):
+        assert relmax(g, e) < 1e-10, (k, relmax(g, e))
+    O = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
+    Or = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
+    assert np.abs(O - Or).max() < 1e-11 * np.abs(Or).max()
