@@ -183,8 +183,8 @@ __host__ __device__ constexpr u64 closure_from_tri(int d, unsigned tri) {
     return out;
 }
 template <int D, u64 CM> struct Pat {
-    static constexpr int nnz = cx_popc(CM);
     static constexpr bool full = (CM == full_cmask<D>());
+    static constexpr int nnz = full ? D * D : cx_popc(CM);
     // patterns are only representable for d*d <= 64; larger d always use the full (dense) pattern
     __host__ __device__ static constexpr bool has(int i, int j) { return full || ((i + D * j) < 64 && ((CM >> ((i + D * j) & 63)) & 1ull)); }
     __host__ __device__ static constexpr int idx(int i, int j) { return full ? (i + D * j) : cx_popc(CM & ((1ull << ((i + D * j) & 63)) - 1ull)); }
