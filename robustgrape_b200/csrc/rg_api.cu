@@ -254,6 +254,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_CHUNK")) pr->chunk_override = atoi(s);
     if (const char* s = getenv("RG_DENSE")) pr->force_dense = atoi(s);
     if (const char* s = getenv("RG_GROUP")) pr->force_group = atoi(s);
+    if (const char* s = getenv("RG_GROUP_SWEEPS")) pr->force_group_sweeps = atoi(s);
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
     if (P.hermitian && d <= 5 && P.nterms <= RG_T_MAX_TERMS) {
         const int npos = d * (d + 1) / 2;
@@ -294,6 +295,16 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         for (int e = 0; e < P.e; ++e) all |= tp.maskErr[e];
         pr->tri_density = (double)__builtin_popcount(all) / npos;
         pr->tri_union = all;
+        // The thread-per-chunk gradient sweep keeps the co-state G = K B inside the closure pattern, which holds only
+        // if the projector and every target entry lie inside it (true for diagonal projectors/targets).
+        const u64 cm = closure_from_tri(d, all);
+        bool inside = true;
+        for (int j = 0; j < d && inside; ++j)
+            for (int i = 0; i < d; ++i)
+                if (P0[i + d * j] != 0.0 && !((cm >> (i + d * j)) & 1ull)) { inside = false; break; }
+        for (auto& en : te)
+            if (!((cm >> (en.row + d * en.col)) & 1ull)) inside = false;
+        pr->costate_in_pattern = inside ? 1 : 0;
         pr->tri_ok = 1;
     }
     if (cudaGetLastError() != cudaSuccess || !P.terms || !P.table) return fail(RG_ERR_CUDA, "descriptor upload failed");

@@ -132,10 +132,15 @@ __device__ inline void term_coef(const DevTerm& t, const EvalCtx& c, int pspace,
 
 // Taylor degree for ||A||_1 <= theta with remainder below 2^-53 (expm section).
 __device__ __forceinline__ int taylor_degree(double nrm) {
+    // theta_m = ((m+1)! * 2^-53)^(1/(m+1)) with a 10 % margin
     if (nrm <= 1.5e-3) return 4;
+    if (nrm <= 6.0e-3) return 5;
     if (nrm <= 1.6e-2) return 6;
+    if (nrm <= 3.4e-2) return 7;
     if (nrm <= 6.5e-2) return 8;
+    if (nrm <= 0.105) return 9;
     if (nrm <= 0.16) return 10;
+    if (nrm <= 0.225) return 11;
     if (nrm <= 0.31) return 12;
     if (nrm <= 0.52) return 14;
     if (nrm <= 0.78) return 16;

@@ -68,10 +68,12 @@ struct rg_problem {
     int chunk_override = 0;
     int force_dense = 0;      // RG_DENSE=1: treat H as dense (no structural-zero skipping)
     int force_group = 0;      // RG_GROUP=1: force the group-per-chunk k_steps kernel
+    int force_group_sweeps = 0;   // RG_GROUP_SWEEPS=1: group (shared-memory) versions of k_chunk_agg / k_grad
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
     double tri_density = 1.0;
     unsigned tri_union = 0;   // union of all structural masks
+    int costate_in_pattern = 0;   // projector and target lie inside the closure pattern
     // workspaces
     DevBuf ws, Qb, Wlb, Cb, Wb, Gb, G1b, H1b, F, F2, addT, addS, F2dx, Fdx, coeff, dX, dOut, dOut2, dO, dFreq, dM;
     int has_target = 0;
@@ -193,6 +195,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
 
     // ---- K1: step propagators + first-order differences (+ chunk aggregates)
     constexpr bool kThreadOK = (D <= 5);
+    constexpr bool kSparseThread = (PID != PAT_FULL) && (Pat<D, CM>::nnz <= 12);   // state fits one thread's registers
     const bool fast = kThreadOK && pr->tri_ok && !pr->force_group;
     if (!fast && PID != PAT_FULL) RG_FAIL(ctx, RG_ERR_INVALID, "internal: structural pattern without the fast path");
     if (fast) {
@@ -206,16 +209,22 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             KTimer kt(ctx, RG_K_STEPS);
             k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
         }
-        const int gs = kagg_group_stride(D, ne);
-        int wpc = 4;
-        while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
-        const size_t smem2 = (size_t)wpc * G * gs * cb;
-        int rc = set_smem(ctx, k_chunk_agg<D, CM>, smem2);
-        if (rc) return rc;
         const long long citems = (long long)B * nc;
-        const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
-        KTimer kt(ctx, RG_K_AGG);
-        k_chunk_agg<D, CM><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+        if (kSparseThread && !pr->force_group_sweeps) {
+            // sparse pattern: whole matrices in one thread's registers, no shared memory
+            KTimer kt(ctx, RG_K_AGG);
+            k_chunk_agg_t<D, CM><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+        } else {
+            const int gs = kagg_group_stride(D, ne);
+            int wpc = 4;
+            while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
+            const size_t smem2 = (size_t)wpc * G * gs * cb;
+            int rc = set_smem(ctx, k_chunk_agg<D, CM>, smem2);
+            if (rc) return rc;
+            const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
+            KTimer kt(ctx, RG_K_AGG);
+            k_chunk_agg<D, CM><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+        }
     } else {
         const int gs = k1_group_stride(D, P.nterms, ne);
         const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
@@ -273,7 +282,11 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     if (want_grad) {
         // ---- K3: backward gradient sweeps (fidelity role, then one role per error source)
         const long long items = (long long)B * nc;
-        {
+        if (kSparseThread && fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
+            KTimer kt(ctx, RG_K_GRAD);
+            k_grad_t<D, CM><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+                pr->Gb.as<cplx>(), iFdx, sign0 * P.inv_eps / DD1, pr->addS.as<double>());
+        } else {
             const int gs = k3_group_stride(D, 1 + P.nvar);
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;

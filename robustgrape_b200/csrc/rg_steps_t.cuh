@@ -375,6 +375,167 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
         }
 }
 
+
+// ------------------------------------------------------------------ thread-per-chunk kernels (sparse patterns)
+// For structural patterns with few non-zeros the whole forward state / co-state fits in one thread's registers,
+// so the chunk aggregate and the backward gradient sweep need no shared memory, no cp.async staging and no
+// cross-lane reduction: one thread = one (pulse, chunk); step matrices stream from HBM in the compact layout.
+template <int D, u64 CM>
+struct PMat {                       // matrix restricted to the pattern, stored compactly
+    cplx v[Pat<D, CM>::nnz];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = cmk(0.0, 0.0);
+    }
+    __device__ __forceinline__ void identity() {
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (Pat<D, CM>::has(i, j)) v[Pat<D, CM>::idx(i, j)] = cmk(i == j ? 1.0 : 0.0, 0.0);
+    }
+    __device__ __forceinline__ void load(const cplx* __restrict__ p) {
+#pragma unroll
+        for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = p[i];
+    }
+};
+// dense d x d (column-major) <-> pattern
+template <int D, u64 CM>
+__device__ __forceinline__ void pmat_from_dense(PMat<D, CM>& m, const cplx* __restrict__ p) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (Pat<D, CM>::has(i, j)) m.v[Pat<D, CM>::idx(i, j)] = p[i + D * j];
+}
+template <int D, u64 CM>
+__device__ __forceinline__ void pmat_to_dense(const PMat<D, CM>& m, cplx* __restrict__ p) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) p[i + D * j] = Pat<D, CM>::has(i, j) ? m.v[Pat<D, CM>::idx(i, j)] : cmk(0.0, 0.0);
+}
+// C = op(A) B with op = none (ADJ = false) or conjugate transpose (ADJ = true); the closure pattern is closed under
+// products and adjoints, so the result stays inside it.
+template <int D, u64 CM, bool ADJ, bool ACC>
+__device__ __forceinline__ void pmat_mul(PMat<D, CM>& c, const PMat<D, CM>& a, const PMat<D, CM>& b) {
+    typedef Pat<D, CM> PT;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (!PT::has(i, j)) continue;
+            cplx acc = ACC ? c.v[PT::idx(i, j)] : cmk(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                if (!PT::has(k, j)) continue;
+                if (ADJ) { if (PT::has(k, i)) cfma_conj(acc, a.v[PT::idx(k, i)], b.v[PT::idx(k, j)]); }
+                else { if (PT::has(i, k)) cfma(acc, a.v[PT::idx(i, k)], b.v[PT::idx(k, j)]); }
+            }
+            c.v[PT::idx(i, j)] = acc;
+        }
+}
+// Re tr(A B)
+template <int D, u64 CM>
+__device__ __forceinline__ double pmat_retrace(const PMat<D, CM>& a, const PMat<D, CM>& b) {
+    typedef Pat<D, CM> PT;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (PT::has(i, j) && PT::has(j, i)) {
+                const cplx x = a.v[PT::idx(i, j)], y = b.v[PT::idx(j, i)];
+                s = fma(x.x, y.x, s); s = fma(-x.y, y.y, s);
+            }
+    return s;
+}
+
+// Chunk aggregates, one thread per (pulse, chunk): Q <- U_k Q ; Wl_e <- U_k Wl_e + D_k^e Q_old
+template <int D, u64 CM>
+__global__ void __launch_bounds__(128)
+k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb) {
+    typedef Pat<D, CM> PT;
+    typedef PMat<D, CM> M;
+    constexpr int DD = D * D;
+    const long long total = (long long)B * nc;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= total) return;
+    const int b = (int)(item / nc), ch = (int)(item % nc);
+    const int nv = P.nvar, ne = P.e;
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    M q; q.identity();
+    if (ne == 0) {
+        M u; u.load(wsb + (size_t)k0 * P.nstore * PT::nnz);
+        for (int k = k0; k < k1; ++k) {
+            M un;
+            if (k + 1 < k1) un.load(wsb + (size_t)(k + 1) * P.nstore * PT::nnz);      // prefetch
+            M qn; pmat_mul<D, CM, false, false>(qn, u, q);
+            q = qn; u = un;
+        }
+    } else {
+        // error aggregates are processed one error source at a time to bound registers (Q is recomputed)
+        for (int e = 0; e < ne; ++e) {
+            q.identity();
+            M wl; wl.zero();
+            for (int k = k0; k < k1; ++k) {
+                const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
+                M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + e) * PT::nnz);
+                M wn; pmat_mul<D, CM, false, false>(wn, u, wl); pmat_mul<D, CM, false, true>(wn, de, q);
+                M qn; pmat_mul<D, CM, false, false>(qn, u, q);
+                wl = wn; q = qn;
+            }
+            pmat_to_dense<D, CM>(wl, Wlb + (((size_t)b * nc + ch) * ne + e) * DD);
+        }
+    }
+    pmat_to_dense<D, CM>(q, Qb + ((size_t)b * nc + ch) * DD);
+}
+
+// Backward gradient sweep, one thread per (pulse, chunk), fidelity role only (ERR roles use k_grad):
+//   out0[b*nx + p*k + v] = scale0 * Re tr(G_k dU_k^v C_{k-1})
+template <int D, u64 CM>
+__global__ void __launch_bounds__(128)
+k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, const cplx* __restrict__ Cb,
+         const cplx* __restrict__ Gb, double* __restrict__ out0, double scale0, double* __restrict__ addS) {
+    typedef Pat<D, CM> PT;
+    typedef PMat<D, CM> M;
+    constexpr int DD = D * D;
+    const long long total = (long long)B * nc;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= total) return;
+    const int b = (int)(item / nc), ch = (int)(item % nc);
+    const int nv = P.nvar, ne = P.e;
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    M c, g;
+    pmat_from_dense<D, CM>(c, Cb + ((size_t)b * nc + ch) * DD);
+    {   // k_scan stores the co-state by rows (row l contiguous): G(i,j) = Gb[i*D + j]
+        const cplx* gp = Gb + ((size_t)b * nc + ch) * DD;
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (PT::has(i, j)) g.v[PT::idx(i, j)] = gp[i * D + j];
+    }
+    M u; u.load(wsb + (size_t)(k1 - 1) * P.nstore * PT::nnz);
+    for (int k = k1 - 1; k >= k0; --k) {
+        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
+        M un;
+        if (k > k0) un.load(wsb + (size_t)(k - 1) * P.nstore * PT::nnz);       // prefetch the next step's U
+        M cp; pmat_mul<D, CM, true, false>(cp, u, c);                         // C_{k-1} = U_k^dag C_k
+        for (int v = 0; v < nv; ++v) {
+            M du; du.load(wsk + (size_t)(1 + v) * PT::nnz);
+            M t; pmat_mul<D, CM, false, false>(t, du, cp);                    // dU C_{k-1}
+            const double s = pmat_retrace<D, CM>(g, t) * scale0;
+            if (P.var_space[v] == RG_S_MAIN) out0[(size_t)b * P.nx + (size_t)P.p * k + P.var_index[v]] = s;
+            else addS[(((size_t)b * (1 + ne)) * P.a + P.var_index[v]) * P.N + k] = s;
+        }
+        M gn; pmat_mul<D, CM, false, false>(gn, g, u);                        // G_{k-1} = G_k U_k
+        g = gn; c = cp; u = un;
+    }
+}
+
 // Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
 template <int D, u64 CM>
 __global__ void __launch_bounds__(128)

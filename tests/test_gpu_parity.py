@@ -339,3 +339,21 @@ def test_nine_level_rydberg_model(gpu_ctx):
     O = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
     Or = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
     assert np.abs(O - Or).max() < 1e-11 * np.abs(Or).max()
+
+
+def test_structured_path_with_non_diagonal_target_and_projector(gpu_ctx):
+    """The CZ Hamiltonian takes the structured fast path, but a dense target / non-diagonal projector puts the
+    co-state outside the Hamiltonian's block pattern: the library must notice and use the general gradient sweep."""
+    from robustgrape_b200.descriptors import ConstantTarget
+    from robustgrape_b200 import rydberg_tools as rt
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rng.normal(size=(5, 5)) + 1j * rng.normal(size=(5, 5)))
+    proj = np.diag([1.0, 2, 1, 0, 0]); proj[0, 1] = 0.5; proj[1, 0] = 0.5
+    up = rg.UnitaryRobustGRAPEProblem(t0=1.3, ntimes=40, ndim=5, H0=rt.rydberg_h0(), nb_additional_param=1,
+                                      error_sources=[rg.ErrorSource(rt.rydberg_amplitude_error())])
+    fp = rg.FidelityRobustGRAPEProblem(up, proj, ConstantTarget(q))
+    x = random_pulse(fp, 1, 2)
+    got = rg.calculate_fidelity_and_derivatives(fp, x)
+    ref = ro.calculate_fidelity_and_derivatives(fp, x)
+    assert abs(got[0] - ref[0]) < 1e-12
+    assert relmax(got[1], ref[1]) < 2e-5 and relmax(got[2], ref[2]) < 2e-5 and relmax(got[3], ref[3]) < 2e-4
