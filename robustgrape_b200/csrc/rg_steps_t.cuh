@@ -188,10 +188,14 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
         }
         if (o == 0) {
             // ||A||_1 <= max_k sum_t |c_t| * ||M_t[:,k]||_1
+            // |c| <= max(|re|,|im|) + (sqrt2 - 1) min(|re|,|im|)  (strict upper bound, <= 8.3 % high; no square roots)
             double nrm = 0.0;
             for (int kk = 0; kk < D; ++kk) {
                 double s = 0.0;
-                for (int t = 0; t < nt; ++t) { const cplx c = ca[t]; s += sqrt(c.x * c.x + c.y * c.y) * sp.colw[t * D + kk]; }
+                for (int t = 0; t < nt; ++t) {
+                    const double ax = fabs(ca[t].x), ay = fabs(ca[t].y);
+                    s += (fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay)) * sp.colw[t * D + kk];
+                }
                 nrm = fmax(nrm, s);
             }
             m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
@@ -363,7 +367,10 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
                 double nrm = 0.0;
                 for (int kk = 0; kk < D; ++kk) {
                     double s = 0.0;
-                    for (int t = 0; t < nt; ++t) { const cplx c = cA[t]; s += sqrt(c.x * c.x + c.y * c.y) * sp.colw[t * D + kk]; }
+                    for (int t = 0; t < nt; ++t) {
+                        const double ax = fabs(cA[t].x), ay = fabs(cA[t].y);
+                        s += (fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay)) * sp.colw[t * D + kk];
+                    }
                     nrm = fmax(nrm, s);
                 }
                 m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
