@@ -66,6 +66,15 @@ def k_steps_flops(N, taylor_m, structured):
     return per_step * N
 
 
+def taylor_degree_for(nrm):
+    """Mirror of taylor_degree() in csrc/rg_common.cuh (the kernel bounds ||dt*H||_1 within 8.3 % from above)."""
+    for th, m in ((1.5e-3, 4), (6.0e-3, 5), (1.6e-2, 6), (3.4e-2, 7), (6.5e-2, 8), (0.105, 9), (0.16, 10), (0.225, 11), (0.31, 12),
+                  (0.52, 14), (0.78, 16), (1.10, 18)):
+        if nrm <= th:
+            return m
+    return 12
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region (pynvml)."""
 
@@ -317,7 +326,7 @@ def main():
             os.environ.pop("RG_DENSE", None)
 
     if rank == 0:
-        m = 6 if args.ntimes >= 400 else (8 if args.ntimes >= 90 else 10)     # Taylor degree the kernel picks for dt*||H||_1
+        m = taylor_degree_for(T0 / N * 0.7071067811865476 * 1.0826 * 1.001 + 2e-4 * T0 / N)   # what the kernel picks
         canonical = canonical_flops(5, N, 1, 1, args.nerr)
         k1_ms, k1_n = timing["k_steps"]
         k1_avg = k1_ms / max(1, k1_n)

@@ -26,6 +26,13 @@ __constant__ double c_inv_j[32] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5,
                                    1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
                                    1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31};
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 enum { VK_DX = 0, VK_ERR = 1, VK_ERR_DX = 2, VK_BASE = 3, VK_TGT = 4, VK_TGT_DX = 5 };
 enum { OPN = 0, OPC = 1, OPT = 2 };
 
@@ -38,7 +45,8 @@ __host__ __device__ inline int k1_group_stride(int D, int nterms, int ne) {
 __host__ __device__ inline int k1b_group_stride(int D, int nterms) { return rg_odd(5 * D * D + 4 * nterms); }
 __host__ __device__ inline int kagg_group_stride(int D, int ne) { return rg_odd((2 * (1 + ne) + ne) * D * D + 1); }
 __host__ __device__ inline int kmat_group_stride(int D, int nload) { return rg_odd((nload + 2) * D * D + 1); }
-__host__ __device__ inline int k2_group_stride(int D) { return rg_odd(14 * D * D + D + 1); }
+#define RG_SCAN_RING 4
+__host__ __device__ inline int k2_group_stride(int D) { return rg_odd((14 + 2 * RG_SCAN_RING) * D * D + D + 1); }
 __host__ __device__ inline int k3_group_stride(int D, int nload) { return rg_odd(2 * nload * D * D + D + 1); }
 
 template <int D> struct GroupInfo {
@@ -712,20 +720,25 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
 // ======================================================================================
 // K2: per-pulse scan over chunk aggregates, fidelity algebra, co-state seeds
 // ======================================================================================
-template <int D>
-__device__ __forceinline__ cplx melem(const cplx* A, int op, int i, int k) {
-    if (op == OPN) return A[i + D * k];
+template <int D, int OP>
+__device__ __forceinline__ cplx melem(const cplx* A, int i, int k) {
+    if (OP == OPN) return A[i + D * k];
     const cplx a = A[k + D * i];
-    return (op == OPC) ? cconj(a) : a;
+    return (OP == OPC) ? cconj(a) : a;
 }
 // column l of dst (+)= alpha * op(A) op(B); dst must not alias A or B.
-template <int D>
-__device__ inline void gmm(cplx* dst, const cplx* A, int opA, const cplx* B, int opB, int l, unsigned amask,
-                           bool accumulate = false, double alpha = 1.0) {
+template <int D, int OPA, int OPB>
+__device__ __forceinline__ void gmm(cplx* dst, const cplx* A, const cplx* B, int l, unsigned amask,
+                                    bool accumulate = false, double alpha = 1.0) {
     __syncwarp(amask);
+    cplx bcol[D];                       // column l of op(B), loaded once
+#pragma unroll
+    for (int k = 0; k < D; ++k) bcol[k] = melem<D, OPB>(B, k, l);
+#pragma unroll
     for (int i = 0; i < D; ++i) {
         cplx acc = cmk(0.0, 0.0);
-        for (int k = 0; k < D; ++k) cfma(acc, melem<D>(A, opA, i, k), melem<D>(B, opB, k, l));
+#pragma unroll
+        for (int k = 0; k < D; ++k) cfma(acc, melem<D, OPA>(A, i, k), bcol[k]);
         acc = cscale(acc, alpha);
         dst[i + D * l] = accumulate ? cadd(dst[i + D * l], acc) : acc;
     }
@@ -743,11 +756,12 @@ __device__ inline cplx greduce(cplx v, cplx* scratch, int l, unsigned amask) {
     return s;
 }
 // tr(op(A) op(B))
-template <int D>
-__device__ inline cplx gtrace2(const cplx* A, int opA, const cplx* B, int opB, cplx* scratch, int l, unsigned amask) {
+template <int D, int OPA, int OPB>
+__device__ __forceinline__ cplx gtrace2(const cplx* A, const cplx* B, cplx* scratch, int l, unsigned amask) {
     __syncwarp(amask);
     cplx acc = cmk(0.0, 0.0);
-    for (int k = 0; k < D; ++k) cfma(acc, melem<D>(A, opA, l, k), melem<D>(B, opB, k, l));
+#pragma unroll
+    for (int k = 0; k < D; ++k) cfma(acc, melem<D, OPA>(A, l, k), melem<D, OPB>(B, k, l));
     return greduce<D>(acc, scratch, l, amask);
 }
 
@@ -804,22 +818,34 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
     cplx c[D], w[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) { c[i] = cmk(i == l ? 1.0 : 0.0, 0.0); w[i] = cmk(0.0, 0.0); }
-    for (int ch = 0; ch < nc; ++ch) {
+    // chunk aggregates stream through a depth-RG_SCAN_RING cp.async ring so DRAM latency overlaps the matvecs
+    cplx* ringQ = scratch + D + 1;
+    cplx* ringW = ringQ + RG_SCAN_RING * DD;
+    auto issue = [&](int ch, int slot) {
         const cplx* q = Qb + ((size_t)b * nc + ch) * DD + l * D;
 #pragma unroll
-        for (int i = 0; i < D; ++i) mX[i + D * l] = q[i];
+        for (int i = 0; i < D; ++i) cp_async16(ringQ + slot * DD + l * D + i, q + i);
         if (role > 0) {
             const cplx* ww = Wlb + (((size_t)b * nc + ch) * ne + es) * DD + l * D;
 #pragma unroll
-            for (int i = 0; i < D; ++i) mW[i + D * l] = ww[i];
+            for (int i = 0; i < D; ++i) cp_async16(ringW + slot * DD + l * D + i, ww + i);
         }
+    };
+    for (int s2 = 0; s2 < RG_SCAN_RING - 1; ++s2) { if (s2 < nc) issue(s2, s2); cp_async_commit(); }
+    for (int ch = 0; ch < nc; ++ch) {
+        const int nx2 = ch + RG_SCAN_RING - 1;
+        if (nx2 < nc) issue(nx2, nx2 % RG_SCAN_RING);
+        cp_async_commit();
+        cp_async_wait<RG_SCAN_RING - 1>();
         __syncwarp(amask);
+        const cplx* cX = ringQ + (ch % RG_SCAN_RING) * DD;
+        const cplx* cW = ringW + (ch % RG_SCAN_RING) * DD;
         cplx cn[D];
-        matvec<D>(mX, c, cn);
+        matvec<D>(cX, c, cn);
         if (role > 0) {
             cplx wn[D];
-            matvec<D>(mX, w, wn);         // Q w
-            matvec_acc<D>(mW, c, wn);     // + Wl c_old
+            matvec<D>(cX, w, wn);         // Q w
+            matvec_acc<D>(cW, c, wn);     // + Wl c_old
 #pragma unroll
             for (int i = 0; i < D; ++i) w[i] = wn[i];
         }
@@ -838,6 +864,7 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
         }
         __syncwarp(amask);
     }
+    cp_async_wait<0>();
 
     if (materialize) {
         if (live) {
@@ -909,19 +936,19 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
         assemble_col<D>(P.tents, P.tcolptr, coef, mU0, l);
     }
     const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
-    gmm<D>(mM, mU0, OPC, mU, OPN, l, amask);              // M = U0^dag U   (or U0^dag E)
-    gmm<D>(T1, cPP, OPN, mM, OPN, l, amask);              // T1 = PP M
+    gmm<D, OPC, OPN>(mM, mU0, mU, l, amask);              // M = U0^dag U   (or U0^dag E)
+    gmm<D, OPN, OPN>(T1, cPP, mM, l, amask);              // T1 = PP M
     cplx tau = cmk(0.0, 0.0);
     {
         cplx d = T1[l + D * l];
         tau = greduce<D>(d, scratch, l, amask);
     }
-    gmm<D>(T2, cP, OPN, mM, OPC, l, amask);               // T2 = P M^dag
-    const cplx tr12 = gtrace2<D>(T1, OPN, T2, OPN, scratch, l, amask);
+    gmm<D, OPN, OPC>(T2, cP, mM, l, amask);               // T2 = P M^dag
+    const cplx tr12 = gtrace2<D, OPN, OPN>(T1, T2, scratch, l, amask);
     double Fval = (tr12.x + tau.x * tau.x + tau.y * tau.y) / DD1;
-    gmm<D>(T3, T2, OPN, cPP, OPN, l, amask);              // P M^dag PP
-    gmm<D>(T4, cP, OPT, mM, OPC, l, amask);               // P^T M^dag
-    gmm<D>(T3, T4, OPN, cPPt, OPN, l, amask, true);       // + P^T M^dag PP^T
+    gmm<D, OPN, OPN>(T3, T2, cPP, l, amask);              // P M^dag PP
+    gmm<D, OPT, OPC>(T4, cP, mM, l, amask);               // P^T M^dag
+    gmm<D, OPN, OPN>(T3, T4, cPPt, l, amask, true);       // + P^T M^dag PP^T
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         cplx v = T3[i + D * l];
@@ -929,17 +956,17 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
         v.x += 2.0 * tau.x * pp; v.y += -2.0 * tau.y * pp;   // + 2 conj(tau) PP
         T3[i + D * l] = v;
     }
-    gmm<D>(mK, T3, OPN, mU0, OPC, l, amask);              // K = R U0^dag
+    gmm<D, OPN, OPC>(mK, T3, mU0, l, amask);              // K = R U0^dag
     double scale_out = 1.0;
     if (role > 0) {
         // F_d2err = 2 [ Re tr(PP ME P ME^dag) - (1+D) Re tr(PP E^dag E) + |tau_e|^2 ] / (D(D+1))
-        gmm<D>(T4, mU, OPC, mU, OPN, l, amask);           // E^dag E
-        const cplx tee = gtrace2<D>(cPP, OPN, T4, OPN, scratch, l, amask);
+        gmm<D, OPC, OPN>(T4, mU, mU, l, amask);           // E^dag E
+        const cplx tee = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
         Fval = 2.0 * (tr12.x - (1.0 + Dt) * tee.x + tau.x * tau.x + tau.y * tau.y) / DD1;
         // K' = K - (1+D) (PP + PP^T) E^dag
 #pragma unroll
         for (int i = 0; i < D; ++i) T4[i + D * l] = cmk(P.PP[i + D * l] + P.PPt[i + D * l], 0.0);
-        gmm<D>(mK, T4, OPN, mU, OPC, l, amask, true, -(1.0 + Dt));
+        gmm<D, OPN, OPC>(mK, T4, mU, l, amask, true, -(1.0 + Dt));
         scale_out = 2.0;
     }
     if (live && l == 0) {
@@ -958,13 +985,13 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
         }
         __syncwarp(amask);
         assemble_col<D>(P.tents, P.tcolptr, coef, mV, l);
-        gmm<D>(mW, mV, OPC, mU, OPN, l, amask);           // S1 = V^dag U
-        const cplx t3 = gtrace2<D>(cPP, OPN, mW, OPN, scratch, l, amask);      // tr(PP V^dag U)
-        gmm<D>(T4, mW, OPN, T2, OPN, l, amask);           // S1 P M^dag
-        const cplx t1 = gtrace2<D>(cPP, OPN, T4, OPN, scratch, l, amask);
-        gmm<D>(mW, mU, OPC, mV, OPN, l, amask);           // U^dag V
-        gmm<D>(T4, cP, OPN, mW, OPN, l, amask);           // P U^dag V
-        const cplx t2 = gtrace2<D>(T1, OPN, T4, OPN, scratch, l, amask);        // tr(PP M P U^dag V)
+        gmm<D, OPC, OPN>(mW, mV, mU, l, amask);           // S1 = V^dag U
+        const cplx t3 = gtrace2<D, OPN, OPN>(cPP, mW, scratch, l, amask);      // tr(PP V^dag U)
+        gmm<D, OPN, OPN>(T4, mW, T2, l, amask);           // S1 P M^dag
+        const cplx t1 = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
+        gmm<D, OPC, OPN>(mW, mU, mV, l, amask);           // U^dag V
+        gmm<D, OPN, OPN>(T4, cP, mW, l, amask);           // P U^dag V
+        const cplx t2 = gtrace2<D, OPN, OPN>(T1, T4, scratch, l, amask);        // tr(PP M P U^dag V)
         const double val = scale_out * (t1.x + t2.x + 2.0 * (tau.x * t3.x + tau.y * t3.y)) / DD1;
         if (live && l == 0) addT[((size_t)b * (1 + ne) + role) * P.a + j] = val;
     }
@@ -974,7 +1001,10 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
     cplx gr[D], hr[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) { gr[j] = mK[l + D * j]; hr[j] = cmk(0.0, 0.0); }
-    for (int ch = nc - 1; ch >= 0; --ch) {
+    __syncwarp(amask);
+    for (int s2 = 0; s2 < RG_SCAN_RING - 1; ++s2) { if (nc - 1 - s2 >= 0) issue(nc - 1 - s2, s2); cp_async_commit(); }
+    for (int it = 0; it < nc; ++it) {
+        const int ch = nc - 1 - it;
         if (live) {
             if (role == 0) {
                 cplx* dst = Gb + ((size_t)b * nc + ch) * DD + l * D;
@@ -987,39 +1017,32 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
                 for (int i = 0; i < D; ++i) { dst[i] = gr[i]; dsh[i] = hr[i]; }
             }
         }
-        const cplx* q = Qb + ((size_t)b * nc + ch) * DD + l * D;
+        const int nx2 = it + RG_SCAN_RING - 1;
+        if (nx2 < nc) issue(nc - 1 - nx2, nx2 % RG_SCAN_RING);
+        cp_async_commit();
+        cp_async_wait<RG_SCAN_RING - 1>();
         __syncwarp(amask);
-#pragma unroll
-        for (int i = 0; i < D; ++i) mX[i + D * l] = q[i];
-        if (role > 0) {
-            const cplx* ww = Wlb + (((size_t)b * nc + ch) * ne + es) * DD + l * D;
-#pragma unroll
-            for (int i = 0; i < D; ++i) mW[i + D * l] = ww[i];
-        }
-        __syncwarp(amask);
+        const cplx* cX = ringQ + (it % RG_SCAN_RING) * DD;
+        const cplx* cW = ringW + (it % RG_SCAN_RING) * DD;
         cplx gn[D];
-        vecmat<D>(gr, mX, gn);
+        vecmat<D>(gr, cX, gn);
         if (role > 0) {
             cplx hn[D];
-            vecmat<D>(hr, mX, hn);        // h Q
-            vecmat_acc<D>(gr, mW, hn);    // + g_old Wl
+            vecmat<D>(hr, cX, hn);        // h Q
+            vecmat_acc<D>(gr, cW, hn);    // + g_old Wl
 #pragma unroll
             for (int i = 0; i < D; ++i) hr[i] = hn[i];
         }
 #pragma unroll
         for (int i = 0; i < D; ++i) gr[i] = gn[i];
+        __syncwarp(amask);
     }
+    cp_async_wait<0>();
 }
 
 // ======================================================================================
 // K3: backward gradient sweep per (pulse, chunk)
 // ======================================================================================
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // sum of a real over the D lanes of a group (lanes base..base+D-1), result valid in lane l==0
 template <int D>
