@@ -19,20 +19,21 @@ k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __rest
     if (l >= D) return;
     cplx* base = smem + staged_desc_bytes(P.nterms, P.nent, D) / sizeof(cplx);
     cplx* mA = base; cplx* mD = base + DD; cplx* mX = base + 2 * DD; cplx* mC = base + 3 * DD; cplx* mE = base + 4 * DD;
-    cplx* coef = base + 5 * DD;      // 2 * nterms
+    cplx* mCi = base + 5 * DD;       // C^{-1} (non-Hermitian H), assembled from the rows each lane carries
+    cplx* coef = base + 6 * DD;      // 2 * nterms
     const int nt = P.nterms;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = x[(size_t)P.p * P.N + j];
-    cplx c[D];
+    cplx c[D], ci[D];                // column l of C, row l of C^{-1}
 #pragma unroll
-    for (int i = 0; i < D; ++i) c[i] = cmk(i == l ? 1.0 : 0.0, 0.0);
+    for (int i = 0; i < D; ++i) { c[i] = cmk(i == l ? 1.0 : 0.0, 0.0); ci[i] = c[i]; }
     for (int t = l; t < nt; t += D) coef[nt + t] = cmk(0.0, 0.0);
     __syncwarp(amask);
     assemble_col<D>(sd.ents, sd.colptr, coef + nt, mD, l, true);     // zero perturbation: only U is needed
     for (int k = 0; k < P.N; ++k) {
         for (int i = 0; i < P.p; ++i) xk[i] = x[(size_t)k * P.p + i];
 #pragma unroll
-        for (int i = 0; i < D; ++i) mC[i + D * l] = c[i];
+        for (int i = 0; i < D; ++i) { mC[i + D * l] = c[i]; mCi[l + D * i] = ci[i]; }
         __syncwarp(amask);
         for (int e = 0; e < P.e; ++e) {
             // Herr_e(eps) / eps : value coefficients without the -i dt factor
@@ -47,7 +48,8 @@ k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __rest
             __syncwarp(amask);
             cplx t1[D], o[D];
             matvec<D>(mE, c, t1);            // column l of Oerr C
-            matvec_adj<D>(mC, t1, o);        // column l of C^dagger Oerr C
+            if (P.hermitian) matvec_adj<D>(mC, t1, o);        // column l of C^dagger Oerr C
+            else matvec<D>(mCi, t1, o);                       // column l of C^{-1} Oerr C
             cplx* dst = O + ((size_t)e * P.N + k) * DD + l * D;
 #pragma unroll
             for (int i = 0; i < D; ++i) dst[i] = o[i];
@@ -93,6 +95,33 @@ k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __rest
 #pragma unroll
         for (int i = 0; i < D; ++i) c[i] = cn[i];
         __syncwarp(amask);
+        if (!P.hermitian) {
+            // C_k^{-1} = C_{k-1}^{-1} U_k^{-1},  U_k^{-1} = exp(-A) (scaled A is still in mA)
+#pragma unroll
+            for (int i = 0; i < D; ++i) { mX[i + D * l] = cmk(-mA[i + D * l].x, -mA[i + D * l].y); }
+            __syncwarp(amask);
+            cplx yi[D], dli[D];
+            horner_fo<D>(mX, mD, l, m, yi, dli);
+            for (int q2 = 0; q2 < sq; ++q2) {
+                __syncwarp(amask);
+#pragma unroll
+                for (int i = 0; i < D; ++i) mE[i + D * l] = yi[i];
+                __syncwarp(amask);
+                cplx yn[D];
+                matvec<D>(mE, yi, yn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) yi[i] = yn[i];
+            }
+            __syncwarp(amask);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mE[i + D * l] = yi[i];
+            __syncwarp(amask);
+            cplx cin[D];
+            vecmat<D>(ci, mE, cin);
+#pragma unroll
+            for (int i = 0; i < D; ++i) ci[i] = cin[i];
+            __syncwarp(amask);
+        }
     }
 }
 

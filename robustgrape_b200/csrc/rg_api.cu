@@ -223,7 +223,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
             pr->any_add_dep = 1;
         }
     }
-    P.nstore = 1 + P.nvar + P.e + P.nvar * P.e;
+    P.nstore = 1 + P.nvar + P.e + P.nvar * P.e + (P.hermitian ? 0 : 1);     // + U^{-1} for non-Hermitian H
 
     P.nterms = (int)ht.size(); P.terms = upload(pr, ht);
     P.nent = (int)he.size(); P.ents = upload(pr, he); P.colptr = upload(pr, hc);

@@ -62,7 +62,6 @@ extern "C" int rg_unitary_and_derivatives(rg_problem* pr, const double* x, doubl
 static int interaction_on_device(rg_problem* pr, const double* x) {
     rg_ctx* ctx = pr->ctx;
     const DevProblem& P = pr->dp;
-    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported yet");
     if (P.e == 0) return RG_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     if (pr->dX.ensure((size_t)P.nx * 8) || pr->dO.ensure((size_t)P.d * P.d * P.N * P.e * sizeof(cplx))) RG_FAIL(ctx, RG_ERR_NOMEM, "device allocation failed");

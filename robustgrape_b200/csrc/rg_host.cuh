@@ -167,7 +167,6 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     const int DD = D * D, ne = P.e, nc = pl.nc, L = pl.L;
     cudaStream_t st = ctx->stream;
     if (!pr->has_target) RG_FAIL(ctx, RG_ERR_INVALID, "problem has no target/projector: fidelity entry points unavailable");
-    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported by the fused path yet");
 
     const size_t cb = sizeof(cplx);
     if (pr->ws.ensure((size_t)B * P.N * P.nstore * WSM * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
@@ -287,7 +286,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             k_grad_t<D, CM><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Gb.as<cplx>(), iFdx, sign0 * P.inv_eps / DD1, pr->addS.as<double>());
         } else {
-            const int gs = k3_group_stride(D, 1 + P.nvar);
+            const int gs = k3_group_stride(D, 1 + P.nvar + (P.hermitian ? 0 : 1));
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
@@ -300,7 +299,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
                 sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
         }
         if (ne > 0) {
-            const int gs = k3_group_stride(D, 2 + 2 * P.nvar);
+            const int gs = k3_group_stride(D, 2 + 2 * P.nvar + (P.hermitian ? 0 : 1));
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
@@ -363,7 +362,6 @@ static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU
     const int DD = D * D, ne = P.e;
     const size_t cb = sizeof(cplx);
     cudaStream_t st = ctx->stream;
-    if (!P.hermitian) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "non-Hermitian Hamiltonians are not supported yet");
     int L = std::max(1, std::min(16, P.N / 64));
     if (pr->chunk_override > 0) L = std::min(pr->chunk_override, P.N);
     const int nc = (P.N + L - 1) / L;
@@ -407,7 +405,7 @@ static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU
                                                    nullptr, nullptr, nullptr, 1, dU, dU_derr);
     }
     {
-        const int nload_max = (ne > 0) ? (2 + 2 * P.nvar) : (1 + P.nvar);
+        const int nload_max = ((ne > 0) ? (2 + 2 * P.nvar) : (1 + P.nvar)) + (P.hermitian ? 0 : 1);
         const int gs = kmat_group_stride(D, nload_max);
         int wpc = 4;
         while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
@@ -433,7 +431,7 @@ template <int D>
 static int launch_interaction(rg_problem* pr, const double* dx, cplx* dO) {
     rg_ctx* ctx = pr->ctx;
     const DevProblem& P = pr->dp;
-    const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(5 * D * D + 2 * P.nterms) * sizeof(cplx);
+    const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(6 * D * D + 2 * P.nterms) * sizeof(cplx);
     int rc = set_smem(ctx, k_interaction_ops<D>, smem);
     if (rc) return rc;
     KTimer kt(ctx, RG_K_ANALYSIS);

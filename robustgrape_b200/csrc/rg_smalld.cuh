@@ -581,6 +581,32 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
                 }
             }
         }
+        if (!P.hermitian) {
+            // U_k^{-1} = exp(-A) (the reference uses inv(), src/UnitaryCalculations.jl:47): one more Horner pass with
+            // -A and a zero perturbation; stored as the last object of the step for the backward sweeps.
+            __syncwarp(amask);
+#pragma unroll
+            for (int i = 0; i < D; ++i) { mX[i + D * l] = cmk(-mA[i + D * l].x, -mA[i + D * l].y); mD[i + D * l] = cmk(0.0, 0.0); }
+            __syncwarp(amask);
+            cplx y[D], dl[D];
+            horner_fo<D>(mX, mD, l, m, y, dl);
+            for (int q2 = 0; q2 < sq; ++q2) {
+                __syncwarp(amask);
+#pragma unroll
+                for (int i = 0; i < D; ++i) mD[i + D * l] = y[i];
+                __syncwarp(amask);
+                cplx yn[D];
+                matvec<D>(mD, y, yn);
+#pragma unroll
+                for (int i = 0; i < D; ++i) y[i] = yn[i];
+            }
+            if (st) {
+                cplx* dst = wsk + (size_t)(P.nstore - 1) * DD + l * D;
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[i] = y[i];
+            }
+            __syncwarp(amask);
+        }
     }
     if (live) {
         cplx* dst = Qb + ((size_t)b * nc + ch) * DD + l * D;
@@ -1081,7 +1107,8 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
     const int es = ERR ? (int)blockIdx.y : -1;
     const int role = es + 1;
     const int nv = P.nvar, ne = P.e;
-    const int nload = ERR ? (2 + 2 * nv) : (1 + nv);
+    const int ninv = P.hermitian ? 0 : 1;                 // extra slot: U_k^{-1} for non-Hermitian H
+    const int nload = (ERR ? (2 + 2 * nv) : (1 + nv)) + ninv;
 
     extern __shared__ cplx smem[];
     cplx* base = smem + (size_t)(warp * G + g) * k3_group_stride(D, nload);
@@ -1109,7 +1136,8 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
         for (int s = 0; s < nload; ++s) {
             int obj = s;
-            if (s == nv + 1) obj = 1 + nv + es;
+            if (ninv && s == nload - 1) obj = P.nstore - 1;
+            else if (s == nv + 1) obj = 1 + nv + es;
             else if (s > nv + 1) obj = 1 + nv + ne + es * nv + (s - nv - 2);
             const cplx* src = wsk + (size_t)obj * PT::nnz + coff;
             cplx* dst = dstbuf + s * DD + l * D;
@@ -1154,7 +1182,13 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         const cplx* mZ = cur;
         const cplx* mDe = cur + (nv + 1) * DD;
         cplx cp[D], gn[D];
-        rewind_advance<D, CM>(mZ, c, gr, cp, gn);           // c_{k-1} = U_k^dag c_k  and  g_{k-1} = g_k U_k in one pass
+        const cplx* mInv = cur + (nload - 1) * DD;
+        if (P.hermitian) {
+            rewind_advance<D, CM>(mZ, c, gr, cp, gn);       // c_{k-1} = U_k^dag c_k  and  g_{k-1} = g_k U_k in one pass
+        } else {
+            matvec<D, CM>(mInv, c, cp);                     // c_{k-1} = U_k^{-1} c_k
+            vecmat<D, CM>(gr, mZ, gn);
+        }
         cplx wp[ERR ? D : 1];
         if (ERR) {
             cplx t[D];
@@ -1162,7 +1196,8 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
 #pragma unroll
             for (int i = 0; i < D; ++i) t[i] = csub(w[ERR ? i : 0], t[i]);
             cplx t2[D];
-            matvec_adj<D, CM>(mZ, t, t2);                   // w_{k-1} = U_k^dag (w_k - D_k c_{k-1})
+            if (P.hermitian) matvec_adj<D, CM>(mZ, t, t2);  // w_{k-1} = U_k^{-1} (w_k - D_k c_{k-1})
+            else matvec<D, CM>(mInv, t, t2);
 #pragma unroll
             for (int i = 0; i < (ERR ? D : 1); ++i) wp[i] = t2[i];
         }
@@ -1247,8 +1282,9 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
     const int ch = (int)item;
     const int role = blockIdx.y, es = role - 1;
     const int nv = P.nvar, ne = P.e;
-    const int nload = (role == 0) ? (1 + nv) : (2 + 2 * nv);
-    const int nload_max = (ne > 0) ? (2 + 2 * nv) : (1 + nv);
+    const int ninv = P.hermitian ? 0 : 1;
+    const int nload = ((role == 0) ? (1 + nv) : (2 + 2 * nv)) + ninv;
+    const int nload_max = ((ne > 0) ? (2 + 2 * nv) : (1 + nv)) + ninv;
 
     extern __shared__ cplx smem[];
     cplx* base = smem + (size_t)(warp * G + g) * kmat_group_stride(D, nload_max);
@@ -1281,7 +1317,8 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
         const cplx* wsk = ws + (size_t)k * P.nstore * PT::nnz;
         for (int s2 = 0; s2 < nload; ++s2) {
             int obj = s2;
-            if (s2 == nv + 1) obj = 1 + nv + es;
+            if (ninv && s2 == nload - 1) obj = P.nstore - 1;
+            else if (s2 == nv + 1) obj = 1 + nv + es;
             else if (s2 > nv + 1) obj = 1 + nv + ne + es * nv + (s2 - nv - 2);
 #pragma unroll
             for (int i = 0; i < D; ++i)
@@ -1294,13 +1331,16 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
         const cplx* mZ = mats;
         const cplx* mDe = mats + (nv + 1) * DD;
         cplx cp[D], gn[D], wp[D];
-        rewind_advance<D>(mZ, c, gr, cp, gn);
+        const cplx* mInv = mats + (nload - 1) * DD;
+        if (P.hermitian) rewind_advance<D>(mZ, c, gr, cp, gn);
+        else { matvec<D>(mInv, c, cp); vecmat<D>(gr, mZ, gn); }
         if (role > 0) {
             cplx t[D];
             matvec<D>(mDe, cp, t);
 #pragma unroll
             for (int i = 0; i < D; ++i) t[i] = csub(w[i], t[i]);
-            matvec_adj<D>(mZ, t, wp);
+            if (P.hermitian) matvec_adj<D>(mZ, t, wp);
+            else matvec<D>(mInv, t, wp);
         }
         for (int v = 0; v < nv; ++v) {
             const cplx* mDv = mats + (1 + v) * DD;

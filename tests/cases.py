@@ -139,3 +139,16 @@ def rydberg9_problem(ntimes, t0, errors=("amp",)):
                          Term(1.0, (Factor.expi(S_ADD, 0, 2.0, math.pi),), ((3, 3, 1.0),), OWNER_TARGET)])
     up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=9, H0=H0, nb_additional_param=1, error_sources=srcs)
     return rg.FidelityRobustGRAPEProblem(up, proj, tgt)
+
+
+def decay_problem(ntimes, t0, gamma=0.05, errors=("amp",)):
+    """Non-Hermitian effective Hamiltonian: CZ drive plus -i gamma/2 on the Rydberg levels.  Legal in the reference
+    because it uses inv(), not the adjoint (src/UnitaryCalculations.jl:47,194)."""
+    base = rt.rydberg_h0()
+    terms = list(base.terms) + [Term(-0.5j * gamma, (), ((3, 3, 1.0), (4, 4, 1.0)), OWNER_H0)]
+    srcs = []
+    for i, e in enumerate(errors):
+        srcs.append(rg.ErrorSource(rt.rydberg_amplitude_error(source=i) if e == "amp" else rt.rydberg_frequency_error(source=i)))
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=5, H0=TermHamiltonian(5, terms), nb_additional_param=1,
+                                      error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, PROJ5, rt.cz_target())

@@ -357,3 +357,33 @@ def test_structured_path_with_non_diagonal_target_and_projector(gpu_ctx):
     ref = ro.calculate_fidelity_and_derivatives(fp, x)
     assert abs(got[0] - ref[0]) < 1e-12
     assert relmax(got[1], ref[1]) < 2e-5 and relmax(got[2], ref[2]) < 2e-5 and relmax(got[3], ref[3]) < 2e-4
+
+
+@pytest.mark.parametrize("N,t0,errors", [(30, 4.0, ("amp", "freq")), (64, 7.613, ()), (6, 60.0, ("amp",))])
+def test_non_hermitian_hamiltonian(gpu_ctx, N, t0, errors):
+    """-i gamma/2 decay on the Rydberg levels: propagators are not unitary, so the backward sweeps rewind with the
+    stored exp(+i dt H) instead of the adjoint (the reference uses inv(), src/UnitaryCalculations.jl:47).
+    The last case also needs scaling-and-squaring."""
+    from cases import decay_problem
+    from oracle import exact_oracle as eo
+    fp = decay_problem(N, t0, 0.08, errors)
+    assert not fp.unitary_problem.H0.is_hermitian()
+    x = random_pulse(fp, 1, 41)
+    got = rg.calculate_fidelity_and_derivatives(fp, x)
+    ref = ro.calculate_fidelity_and_derivatives(fp, x)
+    assert abs(got[0] - ref[0]) < 1e-12
+    for k, g, r, tol in zip(NAMES[1:], got[1:], ref[1:], (2e-5, 2e-5, 2e-4)):
+        assert relmax(g, r) < tol, (k, relmax(g, r))
+    if N <= 30:
+        ex = eo.calculate_fidelity_and_derivatives(fp, x)
+        for k, g, e in zip(NAMES, got, ex):
+            assert relmax(g, e) < (1e-9 if t0 > 20 else 1e-10), (k, relmax(g, e))
+    if errors:
+        O = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
+        Or = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
+        assert np.abs(O - Or).max() < 1e-10 * np.abs(Or).max()
+        U = rg.calculate_unitary_and_derivatives(fp.unitary_problem, x)
+        Ur = ro.calculate_unitary_and_derivatives(fp.unitary_problem, x)
+        assert np.abs(U[0] - Ur[0]).max() < 1e-12
+        assert np.abs(U[1] - Ur[1]).max() < 2e-5 * np.abs(Ur[1]).max()
+        assert np.abs(U[4] - Ur[4]).max() < 2e-4 * np.abs(Ur[4]).max()
