@@ -131,7 +131,7 @@ __device__ __forceinline__ void columns(const cplx (&ta)[Tri<D>::n], const cplx 
 }
 
 template <int D, unsigned UMASK>
-__global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 3)
+__global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 4)
 k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
           int* __restrict__ status) {
     constexpr int NP = Tri<D>::n;
