@@ -161,7 +161,7 @@ def workload_config(args):
                     f"Rydberg, p=1, a=1, e={args.nerr}, t0={T0}, eps=1e-8, eps2=1e-4 (examples/time_optimal_cz.jl)",
         "batch": args.batch, "ntimes": args.ntimes, "nerr": args.nerr,
         "sharding": "pulses over ranks, NCCL all-gather of [cost|grad]",
-        "l2": "each step streams the step-matrix workspace (0.29 MB/pulse written then read twice, 2.4 GB per 8192-pulse batch) -- far larger than the 126 MB L2; no explicit flush",
+        "l2": "each step streams the step-matrix workspace (0.26 MB/pulse written then read twice, 2.1 GB per 8192-pulse batch) -- far larger than the 126 MB L2; no explicit flush",
     }
 
 
@@ -341,7 +341,7 @@ def main():
         if hbm_peak is None:
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
         nstore = 1 + 1 + args.nerr + args.nerr
-        wsm = 9 if args.nerr == 0 else 9          # closure pattern of the CZ model: 9 of 25 elements
+        wsm = 8          # stored pattern of the CZ model: two 2x2 blocks (the untouched |00> level is implicit)
         alg_bytes = Bs * (nx * 8.0 + N * nstore * wsm * 16.0)       # read x, write the step matrices
         achieved = alg_bytes / (k1_avg * 1e-3) / 1e9
         traffic = None
@@ -357,7 +357,7 @@ def main():
             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
-            "note": "structured path: only the 9-element block pattern of the 5x5 step matrices is computed and stored, so the "
+            "note": "structured path: only the 8-element block pattern of the 5x5 step matrices is computed and stored, so the "
                     "kernel is bound by its HBM writes, not by FP64; fp64 sub-object gives the executed-flop rate, "
                     "dense_fp64 the same kernels on a dense-H instantiation",
             "fp64": {"achieved_tflops": min(exec_k1, canonical) * Bs / (k1_avg * 1e-3) / 1e12, "peak_dfma_tflops": peak_dfma,

@@ -40,6 +40,7 @@ struct DevProblem {
     int nx;              // p*N + a
     int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
     int wsm;             // complex elements stored per step matrix (d*d, or the closure pattern's nnz)
+    int wsB;             // pulses in the current launch: the workspace is object-major, ws[obj][b][k][wsm]
     unsigned long long cmask;   // closure pattern of the stored matrices: bit (i + d*j)
 };
 
@@ -186,6 +187,20 @@ __host__ __device__ constexpr u64 closure_from_tri(int d, unsigned tri) {
         for (int i = 0; i < d; ++i)
             if (r[i][j]) out |= 1ull << (i + d * j);
     return out;
+}
+// Stored pattern: the closure minus the diagonal of *inert* levels (levels no term touches, not even on the
+// diagonal): there U(l,l) = 1 and every difference is 0 exactly, so nothing is computed or stored for them.
+// In a stored pattern, level l is inert  <=>  the diagonal bit (l,l) is absent.
+__host__ __device__ constexpr u64 stored_from_tri(int d, unsigned tri) {
+    u64 cm = closure_from_tri(d, tri);
+    for (int l = 0; l < d; ++l) {
+        bool touched = false;
+        for (int k = 0; k < d; ++k)
+            for (int i = 0; i <= k; ++i)
+                if (((tri >> (k * (k + 1) / 2 + i)) & 1u) && (i == l || k == l)) touched = true;
+        if (!touched) cm &= ~(1ull << (l + d * l));
+    }
+    return cm;
 }
 template <int D, u64 CM> struct Pat {
     static constexpr bool full = (CM == full_cmask<D>());

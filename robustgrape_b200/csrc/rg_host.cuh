@@ -151,6 +151,9 @@ template <int D, int PID> constexpr unsigned tri_mask_of() {
 template <int D, int PID> constexpr u64 cmask_of() {
     return (PID == PAT_FULL) ? full_cmask<D>() : closure_from_tri(D, tri_mask_of<D, PID>());
 }
+template <int D, int PID> constexpr u64 smask_of() {      // stored pattern: closure minus inert diagonals
+    return (PID == PAT_FULL) ? full_cmask<D>() : stored_from_tri(D, tri_mask_of<D, PID>());
+}
 
 // Run the fused path for one slab of pulses already resident on the device.
 //   mode 0: fidelity + derivatives  -> dF, dFdx (+1 scale), dF2, dF2dx
@@ -160,9 +163,10 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
                     double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
     rg_ctx* ctx = pr->ctx;
     constexpr u64 CM = cmask_of<D, PID>();
-    constexpr int WSM = Pat<D, CM>::nnz;
+    constexpr u64 CMS = smask_of<D, PID>();
+    constexpr int WSM = Pat<D, CMS>::nnz;
     DevProblem P = pr->dp;
-    P.wsm = WSM; P.cmask = CM;
+    P.wsm = WSM; P.cmask = CMS; P.wsB = B;
     constexpr int G = GroupInfo<D>::G;
     const int DD = D * D, ne = P.e, nc = pl.nc, L = pl.L;
     cudaStream_t st = ctx->stream;
@@ -194,7 +198,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
 
     // ---- K1: step propagators + first-order differences (+ chunk aggregates)
     constexpr bool kThreadOK = (D <= 5);
-    constexpr bool kSparseThread = (PID != PAT_FULL) && (Pat<D, CM>::nnz <= 12);   // state fits one thread's registers
+    constexpr bool kSparseThread = (PID != PAT_FULL) && (Pat<D, CMS>::nnz <= 12);   // state fits one thread's registers
     const bool fast = kThreadOK && pr->tri_ok && !pr->force_group;
     if (!fast && PID != PAT_FULL) RG_FAIL(ctx, RG_ERR_INVALID, "internal: structural pattern without the fast path");
     if (fast) {
@@ -212,17 +216,17 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         if (kSparseThread && !pr->force_group_sweeps) {
             // sparse pattern: whole matrices in one thread's registers, no shared memory
             KTimer kt(ctx, RG_K_AGG);
-            k_chunk_agg_t<D, CM><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+            k_chunk_agg_t<D, CMS><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
         } else {
             const int gs = kagg_group_stride(D, ne);
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem2 = (size_t)wpc * G * gs * cb;
-            int rc = set_smem(ctx, k_chunk_agg<D, CM>, smem2);
+            int rc = set_smem(ctx, k_chunk_agg<D, CM, CMS>, smem2);
             if (rc) return rc;
             const int grid2 = (int)((citems + (long long)wpc * G - 1) / ((long long)wpc * G));
             KTimer kt(ctx, RG_K_AGG);
-            k_chunk_agg<D, CM><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+            k_chunk_agg<D, CM, CMS><<<grid2, wpc * 32, smem2, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
         }
     } else {
         const int gs = k1_group_stride(D, P.nterms, ne);
@@ -283,18 +287,18 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         const long long items = (long long)B * nc;
         if (kSparseThread && fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
             KTimer kt(ctx, RG_K_GRAD);
-            k_grad_t<D, CM><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+            k_grad_t<D, CMS><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Gb.as<cplx>(), iFdx, sign0 * P.inv_eps / DD1, pr->addS.as<double>());
         } else {
             const int gs = k3_group_stride(D, 1 + P.nvar + (P.hermitian ? 0 : 1));
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
-            int rc = set_smem(ctx, k_grad<D, false, CM>, smem);
+            int rc = set_smem(ctx, k_grad<D, false, CM, CMS>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), 1);
             KTimer kt(ctx, RG_K_GRAD);
-            k_grad<D, false, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+            k_grad<D, false, CM, CMS><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
         }
@@ -303,11 +307,11 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
             const size_t smem = (size_t)wpc * G * gs * cb;
-            int rc = set_smem(ctx, k_grad<D, true, CM>, smem);
+            int rc = set_smem(ctx, k_grad<D, true, CM, CMS>, smem);
             if (rc) return rc;
             dim3 grid((unsigned)((items + (long long)wpc * G - 1) / ((long long)wpc * G)), ne);
             KTimer kt(ctx, RG_K_GRAD_ERR);
-            k_grad<D, true, CM><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+            k_grad<D, true, CM, CMS><<<grid, wpc * 32, smem, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 0.0, iF2dx, pr->addS.as<double>());
         }
@@ -357,7 +361,7 @@ static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU
     rg_ctx* ctx = pr->ctx;
     constexpr u64 CM = full_cmask<D>();
     DevProblem P = pr->dp;
-    P.wsm = D * D; P.cmask = CM;
+    P.wsm = D * D; P.cmask = CM; P.wsB = 1;
     constexpr int G = GroupInfo<D>::G;
     const int DD = D * D, ne = P.e;
     const size_t cb = sizeof(cplx);

@@ -448,7 +448,8 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             const int kn = min(k0 + kk + 1, k1 - 1);
             for (int i = 0; i < P.p; ++i) { xk[i] = xnext[i]; xnext[i] = xp[(size_t)kn * P.p + i]; }
         }
-        cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * P.wsm;
+        cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.wsm;          // object 0 of this step
+        const size_t objS = (size_t)P.wsB * P.N * P.wsm;                 // stride between objects
 
         // ---- base matrix A = -i dt H0(x_k)
         fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
@@ -523,7 +524,7 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             }
             if (sq) __syncwarp(amask);
             if (st && nfo > 0) {
-                cplx* dst = wsk + (size_t)(1 + o) * DD + l * D;
+                cplx* dst = wsk + (size_t)(1 + o) * objS + l * D;
 #pragma unroll
                 for (int i = 0; i < D; ++i) dst[i] = dl[i];
             }
@@ -601,7 +602,7 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
                 for (int i = 0; i < D; ++i) y[i] = yn[i];
             }
             if (st) {
-                cplx* dst = wsk + (size_t)(P.nstore - 1) * DD + l * D;
+                cplx* dst = wsk + (size_t)(P.nstore - 1) * objS + l * D;
 #pragma unroll
                 for (int i = 0; i < D; ++i) dst[i] = y[i];
             }
@@ -653,7 +654,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
-    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * P.wsm;
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.wsm;
+    const size_t objS = (size_t)P.wsB * P.N * P.wsm;
 
     fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
     __syncwarp(amask);
@@ -733,7 +735,7 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
                 for (int i = 0; i < D; ++i) mBe[i + D * l] = be_save[i];
             }
             if (live) {
-                cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * P.wsm;
+                cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * objS;
 #pragma unroll
                 for (int i = 0; i < D; ++i) if (pat_has(P.cmask, D, i, l)) dst[pat_idx(P.cmask, D, i, l)] = dab[i];
             }
@@ -1087,7 +1089,7 @@ __device__ __forceinline__ double group_sum0(double v, int lane, int l, unsigned
 //            out1[(b*ne+e)*nx + ...] = (2/DD1) * Re{[g' dU w + h' dU c]/eps^2 + g' d2U c/eps2^2}
 //            (w and h' are built from raw, un-normalised differences, hence 1/eps^2)
 // additional-parameter variables go to addS[((b*(1+ne)+role)*a + j)*N + k] for a later sum over k.
-template <int D, bool ERR, u64 CM>
+template <int D, bool ERR, u64 CM, u64 CMS>
 __global__ void __launch_bounds__(128)
 k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
        const cplx* __restrict__ Cb, const cplx* __restrict__ Wb, const cplx* __restrict__ Gb,
@@ -1114,17 +1116,22 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
     cplx* base = smem + (size_t)(warp * G + g) * k3_group_stride(D, nload);
     cplx* buf0 = base;
     cplx* buf1 = base + nload * DD;
-    typedef Pat<D, CM> PT;
-    // elements outside the pattern are never loaded: zero them once (they stay zero)
+    typedef Pat<D, CMS> PT;            // stored (compact) pattern; CM is the closure used by the products
+    // elements outside the stored pattern are never loaded: set them once (0, or 1 on the diagonal of inert levels
+    // in the propagator slots) -- they keep that value
     if (!PT::full) {
-        for (int s = 0; s < 2 * nload; ++s)
+        for (int s = 0; s < 2 * nload; ++s) {
+            const int sl = s % nload;
+            const bool uslot = (sl == 0) || (ninv && sl == nload - 1);
 #pragma unroll
-            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk(0.0, 0.0);
+            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk((uslot && i == l && !PT::has(l, l)) ? 1.0 : 0.0, 0.0);
+        }
         __syncwarp(amask);
     }
 
     // stored objects this role needs: slot 0 = U, 1..nv = dU^v, [nv+1 = D_e, nv+2.. = d2U^{v,e}]
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     // compact offset of the first stored element of column l, and which rows are stored
     int coff = 0; unsigned rows = 0;
 #pragma unroll
@@ -1133,13 +1140,13 @@ k_grad(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws,
         for (int i = 0; i < D; ++i)
             if (PT::has(i, j)) { if (j < l) ++coff; if (j == l) rows |= 1u << i; }
     auto issue = [&](int k, cplx* dstbuf) {
-        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
+        const cplx* wsk = wsb + (size_t)k * PT::nnz;
         for (int s = 0; s < nload; ++s) {
             int obj = s;
             if (ninv && s == nload - 1) obj = P.nstore - 1;
             else if (s == nv + 1) obj = 1 + nv + es;
             else if (s > nv + 1) obj = 1 + nv + ne + es * nv + (s - nv - 2);
-            const cplx* src = wsk + (size_t)obj * PT::nnz + coff;
+            const cplx* src = wsk + (size_t)obj * objS + coff;
             cplx* dst = dstbuf + s * DD + l * D;
             int r = 0;
 #pragma unroll
@@ -1314,7 +1321,8 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
         const bool ghost = (k0 + kk >= k1);
         const int k = min(k0 + kk, k1 - 1);
         __syncwarp(amask);
-        const cplx* wsk = ws + (size_t)k * P.nstore * PT::nnz;
+        const cplx* wsk = ws + (size_t)k * PT::nnz;
+        const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
         for (int s2 = 0; s2 < nload; ++s2) {
             int obj = s2;
             if (ninv && s2 == nload - 1) obj = P.nstore - 1;
@@ -1322,7 +1330,7 @@ k_materialize(const DevProblem P, int L, int nc, const cplx* __restrict__ ws,
             else if (s2 > nv + 1) obj = 1 + nv + ne + es * nv + (s2 - nv - 2);
 #pragma unroll
             for (int i = 0; i < D; ++i)
-                if (pat_has(CM, D, i, l)) mats[s2 * DD + l * D + i] = wsk[(size_t)obj * PT::nnz + pat_idx(CM, D, i, l)];
+                if (pat_has(CM, D, i, l)) mats[s2 * DD + l * D + i] = wsk[(size_t)obj * objS + pat_idx(CM, D, i, l)];
         }
         // rows of B_k and V_k for the left multiplications
 #pragma unroll

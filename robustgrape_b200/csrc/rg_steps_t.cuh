@@ -114,17 +114,19 @@ __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], cons
 template <int D, unsigned UMASK, int l>
 __device__ __forceinline__ void columns(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD, int m,
                                         bool live, cplx* __restrict__ dstD, cplx* __restrict__ dstU) {
-    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     if constexpr (l < D) {
-        cplx y[D], dl[D];
-        horner_col_tri<D, UMASK, l>(ta, td, mA, mD, m, y, dl);
-        if (live) {
+        if constexpr (PT::has(l, l)) {              // inert levels: U(l,l) = 1, dU = 0, nothing computed or stored
+            cplx y[D], dl[D];
+            horner_col_tri<D, UMASK, l>(ta, td, mA, mD, m, y, dl);
+            if (live) {
 #pragma unroll
-            for (int i = 0; i < D; ++i)
-                if (PT::has(i, l)) {
-                    if (dstD) dstD[PT::idx(i, l)] = dl[i];
-                    if (dstU) dstU[PT::idx(i, l)] = y[i];
-                }
+                for (int i = 0; i < D; ++i)
+                    if (PT::has(i, l)) {
+                        if (dstD) dstD[PT::idx(i, l)] = dl[i];
+                        if (dstU) dstU[PT::idx(i, l)] = y[i];
+                    }
+            }
         }
         columns<D, UMASK, l + 1>(ta, td, mA, mD, m, live, dstD, dstU);
     }
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u
 k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
           int* __restrict__ status) {
     constexpr int NP = Tri<D>::n;
-    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
     const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     const long long total = (long long)B * P.N;
@@ -147,7 +149,8 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
-    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * PT::nnz;
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)PT::nnz;            // object 0 of this step
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;                    // stride between objects
     const int nt = P.nterms, nv = P.nvar, ne = P.e, nfo = nv + ne;
 
     cplx ca[RG_T_MAX_TERMS], cd[RG_T_MAX_TERMS];     // (-i dt) * coefficient, value and difference
@@ -204,7 +207,7 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
         }
         const unsigned mD = (nfo == 0) ? 0u : (o < nv ? tp.maskVar[o] : tp.maskErr[o - nv]);
         // ---- columns (unrolled: the pattern of each column is known at compile time)
-        columns<D, UMASK, 0>(ta, td, tp.maskA, mD, m, live, nfo > 0 ? wsk + (size_t)(1 + o) * PT::nnz : nullptr,
+        columns<D, UMASK, 0>(ta, td, tp.maskA, mD, m, live, nfo > 0 ? wsk + (size_t)(1 + o) * objS : nullptr,
                              o == 0 ? wsk : nullptr);
     }
 }
@@ -250,8 +253,9 @@ template <int D, unsigned UMASK, int l>
 __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cplx (&tal)[Tri<D>::n], const cplx (&tbe)[Tri<D>::n],
                                            const cplx (&tga)[Tri<D>::n], unsigned mA, unsigned mAl, unsigned mBe, int m,
                                            bool live, cplx* __restrict__ dst) {
-    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     if constexpr (l < D) {
+      if constexpr (PT::has(l, l)) {
         cplx y[D], da[D], db[D], dab[D];
         const double inv0 = c_inv_j[m];
         tri_column<D, UMASK, l>(y, ta, inv0);
@@ -304,6 +308,7 @@ __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cp
             for (int i = 0; i < D; ++i)
                 if (PT::has(i, l)) dst[PT::idx(i, l)] = dab[i];
         }
+      }
         so_columns<D, UMASK, l + 1>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
     }
 }
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(128, 2)
 k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
              int* __restrict__ status) {
     constexpr int NP = Tri<D>::n;
-    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
     const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     const long long total = (long long)B * P.N;
@@ -327,7 +332,8 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
-    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)P.nstore * PT::nnz;
+    cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     const int nt = P.nterms, nv = P.nvar, ne = P.e;
 
     cplx cA[RG_T_MAX_TERMS], cB[RG_T_MAX_TERMS], cC[RG_T_MAX_TERMS];
@@ -378,7 +384,7 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
                 if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 2); m = 18; }
             }
             so_columns<D, UMASK, 0>(ta, tal, tbe, tga, tp.maskA, tp.maskVar[v], tp.maskErr[e], m, live,
-                                    wsk + (size_t)(1 + nv + ne + e * nv + v) * PT::nnz);
+                                    wsk + (size_t)(1 + nv + ne + e * nv + v) * objS);
         }
 }
 
@@ -415,12 +421,14 @@ __device__ __forceinline__ void pmat_from_dense(PMat<D, CM>& m, const cplx* __re
         for (int i = 0; i < D; ++i)
             if (Pat<D, CM>::has(i, j)) m.v[Pat<D, CM>::idx(i, j)] = p[i + D * j];
 }
+// unit_inert: entries (l,l) of inert levels (diagonal bit absent) are written as 1 (products of propagators), else 0
 template <int D, u64 CM>
-__device__ __forceinline__ void pmat_to_dense(const PMat<D, CM>& m, cplx* __restrict__ p) {
+__device__ __forceinline__ void pmat_to_dense(const PMat<D, CM>& m, cplx* __restrict__ p, bool unit_inert) {
 #pragma unroll
     for (int j = 0; j < D; ++j)
 #pragma unroll
-        for (int i = 0; i < D; ++i) p[i + D * j] = Pat<D, CM>::has(i, j) ? m.v[Pat<D, CM>::idx(i, j)] : cmk(0.0, 0.0);
+        for (int i = 0; i < D; ++i)
+            p[i + D * j] = Pat<D, CM>::has(i, j) ? m.v[Pat<D, CM>::idx(i, j)] : cmk((i == j && unit_inert) ? 1.0 : 0.0, 0.0);
 }
 // C = op(A) B with op = none (ADJ = false) or conjugate transpose (ADJ = true); the closure pattern is closed under
 // products and adjoints, so the result stays inside it.
@@ -471,13 +479,14 @@ k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__
     const int b = (int)(item / nc), ch = (int)(item % nc);
     const int nv = P.nvar, ne = P.e;
     const int k0 = ch * L, k1 = min(P.N, k0 + L);
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     M q; q.identity();
     if (ne == 0) {
-        M u; u.load(wsb + (size_t)k0 * P.nstore * PT::nnz);
+        M u; u.load(wsb + (size_t)k0 * PT::nnz);
         for (int k = k0; k < k1; ++k) {
             M un;
-            if (k + 1 < k1) un.load(wsb + (size_t)(k + 1) * P.nstore * PT::nnz);      // prefetch
+            if (k + 1 < k1) un.load(wsb + (size_t)(k + 1) * PT::nnz);      // prefetch
             M qn; pmat_mul<D, CM, false, false>(qn, u, q);
             q = qn; u = un;
         }
@@ -487,16 +496,16 @@ k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__
             q.identity();
             M wl; wl.zero();
             for (int k = k0; k < k1; ++k) {
-                const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
-                M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + e) * PT::nnz);
+                const cplx* wsk = wsb + (size_t)k * PT::nnz;
+                M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + e) * objS);
                 M wn; pmat_mul<D, CM, false, false>(wn, u, wl); pmat_mul<D, CM, false, true>(wn, de, q);
                 M qn; pmat_mul<D, CM, false, false>(qn, u, q);
                 wl = wn; q = qn;
             }
-            pmat_to_dense<D, CM>(wl, Wlb + (((size_t)b * nc + ch) * ne + e) * DD);
+            pmat_to_dense<D, CM>(wl, Wlb + (((size_t)b * nc + ch) * ne + e) * DD, false);
         }
     }
-    pmat_to_dense<D, CM>(q, Qb + ((size_t)b * nc + ch) * DD);
+    pmat_to_dense<D, CM>(q, Qb + ((size_t)b * nc + ch) * DD, true);
 }
 
 // Backward gradient sweep, one thread per (pulse, chunk), fidelity role only (ERR roles use k_grad):
@@ -514,7 +523,8 @@ k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, 
     const int b = (int)(item / nc), ch = (int)(item % nc);
     const int nv = P.nvar, ne = P.e;
     const int k0 = ch * L, k1 = min(P.N, k0 + L);
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     M c, g;
     pmat_from_dense<D, CM>(c, Cb + ((size_t)b * nc + ch) * DD);
     {   // k_scan stores the co-state by rows (row l contiguous): G(i,j) = Gb[i*D + j]
@@ -525,14 +535,14 @@ k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, 
             for (int i = 0; i < D; ++i)
                 if (PT::has(i, j)) g.v[PT::idx(i, j)] = gp[i * D + j];
     }
-    M u; u.load(wsb + (size_t)(k1 - 1) * P.nstore * PT::nnz);
+    M u; u.load(wsb + (size_t)(k1 - 1) * PT::nnz);
     for (int k = k1 - 1; k >= k0; --k) {
-        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
+        const cplx* wsk = wsb + (size_t)k * PT::nnz;
         M un;
-        if (k > k0) un.load(wsb + (size_t)(k - 1) * P.nstore * PT::nnz);       // prefetch the next step's U
+        if (k > k0) un.load(wsb + (size_t)(k - 1) * PT::nnz);       // prefetch the next step's U
         M cp; pmat_mul<D, CM, true, false>(cp, u, c);                         // C_{k-1} = U_k^dag C_k
         for (int v = 0; v < nv; ++v) {
-            M du; du.load(wsk + (size_t)(1 + v) * PT::nnz);
+            M du; du.load(wsk + (size_t)(1 + v) * objS);
             M t; pmat_mul<D, CM, false, false>(t, du, cp);                    // dU C_{k-1}
             const double s = pmat_retrace<D, CM>(g, t) * scale0;
             if (P.var_space[v] == RG_S_MAIN) out0[(size_t)b * P.nx + (size_t)P.p * k + P.var_index[v]] = s;
@@ -544,7 +554,7 @@ k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, 
 }
 
 // Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
-template <int D, u64 CM>
+template <int D, u64 CM, u64 CMS>
 __global__ void __launch_bounds__(128)
 k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb) {
     constexpr int G = GroupInfo<D>::G;
@@ -566,14 +576,15 @@ k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ w
     cplx* buf0 = base;
     cplx* buf1 = base + nload * DD;
     cplx* wl = base + 2 * nload * DD + l * D;      // + e*DD, private columns
-    typedef Pat<D, CM> PT;
+    typedef Pat<D, CMS> PT;            // stored (compact) pattern; CM is the closure used by the products
     if (!PT::full) {
         for (int s = 0; s < 2 * nload; ++s)
 #pragma unroll
-            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk(0.0, 0.0);
+            for (int i = 0; i < D; ++i) base[s * DD + l * D + i] = cmk((s % nload == 0 && i == l && !PT::has(l, l)) ? 1.0 : 0.0, 0.0);
         __syncwarp(amask);
     }
-    const cplx* wsb = ws + (size_t)b * P.N * (size_t)P.nstore * PT::nnz;
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     int coff = 0; unsigned rows = 0;
 #pragma unroll
     for (int j = 0; j < D; ++j)
@@ -581,10 +592,10 @@ k_chunk_agg(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ w
         for (int i = 0; i < D; ++i)
             if (PT::has(i, j)) { if (j < l) ++coff; if (j == l) rows |= 1u << i; }
     auto issue = [&](int k, cplx* dstbuf) {
-        const cplx* wsk = wsb + (size_t)k * P.nstore * PT::nnz;
+        const cplx* wsk = wsb + (size_t)k * PT::nnz;
         for (int s = 0; s < nload; ++s) {
             const int obj = (s == 0) ? 0 : (1 + nv + (s - 1));
-            const cplx* src = wsk + (size_t)obj * PT::nnz + coff;
+            const cplx* src = wsk + (size_t)obj * objS + coff;
             cplx* dst = dstbuf + s * DD + l * D;
             int r = 0;
 #pragma unroll
