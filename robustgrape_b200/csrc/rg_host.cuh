@@ -213,11 +213,16 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
             k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
         }
         const long long citems = (long long)B * nc;
-        if (kSparseThread && !pr->force_group_sweeps) {
-            // sparse pattern: whole matrices in one thread's registers, no shared memory
-            KTimer kt(ctx, RG_K_AGG);
-            k_chunk_agg_t<D, CMS><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
-        } else {
+        bool agg_done = false;
+        if constexpr (kSparseThread) {
+            if (!pr->force_group_sweeps) {
+                // sparse pattern: whole matrices in one thread's registers, no shared memory
+                KTimer kt(ctx, RG_K_AGG);
+                k_chunk_agg_t<D, CMS><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());
+                agg_done = true;
+            }
+        }
+        if (!agg_done) {
             const int gs = kagg_group_stride(D, ne);
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
@@ -285,11 +290,24 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     if (want_grad) {
         // ---- K3: backward gradient sweeps (fidelity role, then one role per error source)
         const long long items = (long long)B * nc;
-        if (kSparseThread && fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
-            KTimer kt(ctx, RG_K_GRAD);
-            k_grad_t<D, CMS><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
-                pr->Gb.as<cplx>(), iFdx, sign0 * P.inv_eps / DD1, pr->addS.as<double>());
-        } else {
+        bool grad_done = false, graderr_done = false;
+        if constexpr (kSparseThread) {
+            if (fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
+                {
+                    KTimer kt(ctx, RG_K_GRAD);
+                    k_grad_t<D, CMS><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
+                        pr->Gb.as<cplx>(), iFdx, sign0 * P.inv_eps / DD1, pr->addS.as<double>());
+                }
+                if (ne > 0) {
+                    KTimer kt(ctx, RG_K_GRAD_ERR);
+                    dim3 grid((unsigned)((items + 127) / 128), ne);
+                    k_grad_err_t<D, CMS><<<grid, 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(), pr->Wb.as<cplx>(),
+                                                            pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iF2dx, pr->addS.as<double>());
+                }
+                grad_done = graderr_done = true;
+            }
+        }
+        if (!grad_done) {
             const int gs = k3_group_stride(D, 1 + P.nvar + (P.hermitian ? 0 : 1));
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
@@ -302,7 +320,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
                 pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(), iFdx,
                 sign0 * P.inv_eps / DD1, iF2dx, pr->addS.as<double>());
         }
-        if (ne > 0) {
+        if (ne > 0 && !graderr_done) {
             const int gs = k3_group_stride(D, 2 + 2 * P.nvar + (P.hermitian ? 0 : 1));
             int wpc = 4;
             while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;

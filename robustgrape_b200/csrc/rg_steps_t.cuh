@@ -553,6 +553,80 @@ k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, 
     }
 }
 
+
+// Backward sweep of the sensitivity gradient, one thread per (pulse, chunk), error source e = blockIdx.y:
+//   out1[(b*ne+e)*nx + p*k + v] = (2/DD1) Re{ [tr(G' dU W_{k-1}) + tr(H' dU C_{k-1})]/eps^2 + tr(G' d2U C_{k-1})/eps2^2 }
+// (W and H' carry an un-normalised eps, see k_grad).  Hermitian problems only (rewind with the adjoint).
+template <int D, u64 CM>
+__global__ void __launch_bounds__(128)
+k_grad_err_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, const cplx* __restrict__ Cb,
+             const cplx* __restrict__ Wb, const cplx* __restrict__ G1b, const cplx* __restrict__ H1b,
+             double* __restrict__ out1, double* __restrict__ addS) {
+    typedef Pat<D, CM> PT;
+    typedef PMat<D, CM> M;
+    constexpr int DD = D * D;
+    const long long total = (long long)B * nc;
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= total) return;
+    const int b = (int)(item / nc), ch = (int)(item % nc);
+    const int es = blockIdx.y;
+    const int nv = P.nvar, ne = P.e;
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    const cplx* wsb = ws + (size_t)b * P.N * (size_t)PT::nnz;
+    const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
+    const double DD1 = P.Dtr * (P.Dtr + 1.0);
+    const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
+    M c, w, g, h;
+    pmat_from_dense<D, CM>(c, Cb + ((size_t)b * nc + ch) * DD);
+    {
+        const size_t off = (((size_t)b * ne + es) * nc + ch) * DD;
+        pmat_from_dense<D, CM>(w, Wb + off);
+        const cplx* gp = G1b + off;          // co-states are stored by rows: G(i,j) = gp[i*D + j]
+        const cplx* hp = H1b + off;
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (PT::has(i, j)) { g.v[PT::idx(i, j)] = gp[i * D + j]; h.v[PT::idx(i, j)] = hp[i * D + j]; }
+    }
+    for (int k = k1 - 1; k >= k0; --k) {
+        const cplx* wsk = wsb + (size_t)k * PT::nnz;
+        {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
+            M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + es) * objS);
+            M cp; pmat_mul<D, CM, true, false>(cp, u, c);
+            c = cp;
+            M t; pmat_mul<D, CM, false, false>(t, de, c);
+#pragma unroll
+            for (int i = 0; i < PT::nnz; ++i) t.v[i] = csub(w.v[i], t.v[i]);
+            pmat_mul<D, CM, true, false>(w, u, t);
+        }
+        for (int v = 0; v < nv; ++v) {
+            double s1, s2;
+            {
+                M du; du.load(wsk + (size_t)(1 + v) * objS);
+                M t; pmat_mul<D, CM, false, false>(t, du, c);
+                s1 = pmat_retrace<D, CM>(h, t);
+                pmat_mul<D, CM, false, false>(t, du, w);
+                s1 += pmat_retrace<D, CM>(g, t);
+            }
+            {
+                M d2; d2.load(wsk + (size_t)(1 + nv + ne + es * nv + v) * objS);
+                M t; pmat_mul<D, CM, false, false>(t, d2, c);
+                s2 = pmat_retrace<D, CM>(g, t);
+            }
+            const double s = f1 * s1 + f2 * s2;
+            if (P.var_space[v] == RG_S_MAIN) out1[((size_t)b * ne + es) * P.nx + (size_t)P.p * k + P.var_index[v]] = s;
+            else addS[(((size_t)b * (1 + ne) + 1 + es) * P.a + P.var_index[v]) * P.N + k] = s;
+        }
+        {   // advance: H' <- H' U + G' D ;  G' <- G' U
+            M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + es) * objS);
+            M hn; pmat_mul<D, CM, false, false>(hn, h, u); pmat_mul<D, CM, false, true>(hn, g, de);
+            M gn; pmat_mul<D, CM, false, false>(gn, g, u);
+            h = hn; g = gn;
+        }
+    }
+}
+
 // Chunk aggregates from the stored step matrices: q <- U_k q ; wl_e <- U_k wl_e + D_k^e q_old.
 template <int D, u64 CM, u64 CMS>
 __global__ void __launch_bounds__(128)
