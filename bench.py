@@ -160,7 +160,7 @@ def workload_config(args):
         "workload": f"C4 multi-start CZ: {args.batch} random-init pulses x {args.ntimes} time steps, d=5 symmetric-blockaded "
                     f"Rydberg, p=1, a=1, e={args.nerr}, t0={T0}, eps=1e-8, eps2=1e-4 (examples/time_optimal_cz.jl)",
         "batch": args.batch, "ntimes": args.ntimes, "nerr": args.nerr,
-        "sharding": "pulses over ranks, NCCL all-gather of [cost|grad]",
+        "sharding": "pulses over ranks; NCCL all-gather of [cost|grad] per step, overlapped with the next step's kernels (double-buffered)",
         "l2": "each step streams the step-matrix workspace (0.26 MB/pulse written then read twice, 2.1 GB per 8192-pulse batch) -- far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -217,14 +217,31 @@ def main():
     prob = Problem(make_problem(N, args.nerr), ctx)
 
     dX = torch.from_numpy(Xs).to(dev)                              # inputs resident in HBM
-    out_local = torch.empty(Bs * (1 + nx), dtype=torch.float64, device=dev)   # [cost (Bs) | grad (Bs, nx)]
-    out_all = torch.empty(world * Bs * (1 + nx), dtype=torch.float64, device=dev) if world > 1 else out_local
+    # [cost (Bs) | grad (Bs, nx)] per rank; two buffers so that the all-gather of step i (NCCL's own stream) overlaps the
+    # kernels of step i+1: in multi-start optimisation a rank's next evaluation only needs its own shard's gradients.
+    out_locals = [torch.empty(Bs * (1 + nx), dtype=torch.float64, device=dev) for _ in range(2)]
+    out_alls = [torch.empty(world * Bs * (1 + nx), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else out_locals
+    out_local = out_locals[0]
     dcost, dgrad = out_local[:Bs], out_local[Bs:]
+    pending = [None, None]
+    step_no = [0]
 
     def step():
-        prob.cost_and_grad_batch_dev(Bs, nx, dX.data_ptr(), coeff, dcost.data_ptr(), dgrad.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(out_all, out_local)
+        i = step_no[0] & 1
+        step_no[0] += 1
+        if pending[i] is not None:
+            pending[i].wait()                                      # buffer i is free again (its all-gather finished)
+            pending[i] = None
+        ol = out_locals[i]
+        prob.cost_and_grad_batch_dev(Bs, nx, dX.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr())
+        if world > 1 and not os.environ.get("RG_BENCH_NO_GATHER"):      # (diagnostic switch: compute-only scaling)
+            pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
+
+    def drain():
+        for i in (0, 1):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     def barrier():
         if world > 1:
@@ -237,6 +254,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     ctx.synchronize()
     barrier()
     l0 = ctx.launch_count
@@ -245,6 +263,7 @@ def main():
         e0.record()
         for _ in range(args.steps):
             step()
+        drain()                                                    # every step's all-gather completes inside the timed region
         e1.record()
         barrier()
     launches = ctx.launch_count - l0
@@ -254,7 +273,7 @@ def main():
     ms_total = float(ms.item())
     value = B * args.steps / (ms_total * 1e-3)
     ctx.synchronize()
-    cost_host = dcost.cpu().numpy()
+    cost_host = out_locals[(step_no[0] - 1) & 1][:Bs].cpu().numpy()
 
     # ---- e2e: host buffers through the C ABI, H2D and D2H inside the timed region
     hX = torch.from_numpy(Xs).pin_memory()

@@ -130,10 +130,16 @@ static inline Plan make_plan(const rg_problem* pr, int B) {
     return pl;
 }
 
+// Opt in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is a host-side call of a few microseconds; the
+// largest size requested so far is cached per kernel so that steady-state launches skip it.
 template <class K>
 static int set_smem(rg_ctx* ctx, K kern, size_t bytes) {
     if (bytes > 227 * 1024) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory", bytes);
+    static size_t granted[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // per template instantiation, per device
+    const int dev = ctx->device & 7;
+    if (bytes <= granted[dev]) return RG_OK;
     CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    granted[dev] = bytes;
     return RG_OK;
 }
 
