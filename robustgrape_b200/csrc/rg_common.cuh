@@ -62,6 +62,12 @@ __device__ __forceinline__ void cfma_conj(cplx& acc, cplx a, cplx b) {
     acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
 }
 
+// acc -= conj(a) * b   (the lower-triangle partner of a skew-Hermitian element)
+__device__ __forceinline__ void cfma_nconj(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
 // ---------------------------------------------------------------------------------------
 // Factor value and accurate finite difference.
 //   value  f(v)           (err factors use `errv`)

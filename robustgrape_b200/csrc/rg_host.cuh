@@ -135,11 +135,19 @@ static inline Plan make_plan(const rg_problem* pr, int B) {
 template <class K>
 static int set_smem(rg_ctx* ctx, K kern, size_t bytes) {
     if (bytes > 227 * 1024) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "kernel needs %zu bytes of shared memory", bytes);
-    static size_t granted[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // per template instantiation, per device
-    const int dev = ctx->device & 7;
-    if (bytes <= granted[dev]) return RG_OK;
+    // keyed by (kernel address, device): instantiations with the same signature share the type K
+    struct Granted { const void* fn; int dev; size_t bytes; };
+    static std::vector<Granted> granted;
+    const void* fn = reinterpret_cast<const void*>(kern);
+    for (auto& g : granted)
+        if (g.fn == fn && g.dev == ctx->device) {
+            if (bytes <= g.bytes) return RG_OK;
+            CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            g.bytes = bytes;
+            return RG_OK;
+        }
     CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    granted[dev] = bytes;
+    granted.push_back({fn, ctx->device, bytes});
     return RG_OK;
 }
 
@@ -245,12 +253,12 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         int wpc = 4;
         while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
         const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
-        int rc = set_smem(ctx, k_steps<D, false>, smem);
+        int rc = set_smem(ctx, k_steps<D>, smem);
         if (rc) return rc;
         const long long items = (long long)B * nc;
         const int grid = (int)((items + (long long)wpc * G - 1) / ((long long)wpc * G));
         KTimer kt(ctx, RG_K_STEPS);
-        k_steps<D, false><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+        k_steps<D><<<grid, wpc * 32, smem, st>>>(P, dX, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
                                                        pr->Wlb.as<cplx>(), ctx->d_status);
     }
     // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
@@ -405,10 +413,10 @@ static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU
         int wpc = 4;
         while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
         const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
-        int rc = set_smem(ctx, k_steps<D, false>, smem);
+        int rc = set_smem(ctx, k_steps<D>, smem);
         if (rc) return rc;
         KTimer kt(ctx, RG_K_STEPS);
-        k_steps<D, false><<<(nc + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(P, dx, 1, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+        k_steps<D><<<(nc + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(P, dx, 1, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
                                                                                 pr->Wlb.as<cplx>(), ctx->d_status);
     }
     if (ne > 0 && P.nvar > 0) {

@@ -242,75 +242,13 @@ __device__ __forceinline__ void horner_so(const cplx* mA, const cplx* mAl, const
 
 // ------------------------------------------------------------------ skew-Hermitian fast path
 // For Hermitian H (and Hermitian perturbations) A = -i dt H and dA are skew-Hermitian:
-// M[k][i] = -conj(M[i][k]).  Only the upper triangle is loaded, once per pass, into registers, so the
-// Horner loop runs without any shared-memory traffic (the dense loop above is LSU-wavefront bound:
-// every 16-byte operand costs 4 wavefronts and feeds only 4-8 DFMA).
+// M[k][i] = -conj(M[i][k]).  The thread-per-step kernels (rg_steps_t.cuh) keep only the upper triangles, in
+// registers, so their Horner loops run without any shared-memory traffic (the dense group loop above is
+// LSU-wavefront bound: every 16-byte operand costs 4 wavefronts and feeds only 4-8 DFMA).
 template <int D> struct Tri {
     static constexpr int n = D * (D + 1) / 2;
     __host__ __device__ static constexpr int idx(int i, int k) { return k * (k + 1) / 2 + i; }   // i <= k
 };
-template <int D>
-__device__ __forceinline__ void load_tri(const cplx* M, cplx (&t)[Tri<D>::n]) {
-#pragma unroll
-    for (int k = 0; k < D; ++k)
-#pragma unroll
-        for (int i = 0; i <= k; ++i) t[Tri<D>::idx(i, k)] = M[i + D * k];
-}
-// acc -= conj(a) * b
-__device__ __forceinline__ void cfma_nconj(cplx& acc, cplx a, cplx b) {
-    acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
-    acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
-}
-template <int D>
-__device__ __forceinline__ void horner_fo_tri(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], int l, int m,
-                                              cplx (&y)[D], cplx (&dl)[D]) {
-    // first iteration: Y = I + A/m, Dl = dA/m  -> column l of the (skew-Hermitian) matrices
-    {
-        const double inv = c_inv_j[m];
-#pragma unroll
-        for (int i = 0; i < D; ++i) { y[i] = cmk(0.0, 0.0); dl[i] = cmk(0.0, 0.0); }
-#pragma unroll
-        for (int k = 0; k < D; ++k)
-#pragma unroll
-            for (int i = 0; i <= k; ++i) {
-                const cplx a = ta[Tri<D>::idx(i, k)], d = td[Tri<D>::idx(i, k)];
-                if (k == l) { y[i] = cscale(a, inv); dl[i] = cscale(d, inv); }
-                if (i == l && i != k) { y[k] = cscale(cmk(-a.x, a.y), inv); dl[k] = cscale(cmk(-d.x, d.y), inv); }
-            }
-#pragma unroll
-        for (int i = 0; i < D; ++i) if (i == l) y[i].x += 1.0;
-    }
-    for (int j = m - 1; j >= 1; --j) {
-        const double inv = c_inv_j[j];
-        cplx t[D], u[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) { t[i] = cmk(0.0, 0.0); u[i] = cmk(0.0, 0.0); }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-#pragma unroll
-            for (int i = 0; i <= k; ++i) {
-                const cplx a = ta[Tri<D>::idx(i, k)], d = td[Tri<D>::idx(i, k)];
-                const cplx sk = cadd(y[k], dl[k]);
-                cfma(t[i], a, y[k]);
-                cfma(u[i], a, dl[k]);
-                cfma(u[i], d, sk);
-                if (i != k) {
-                    const cplx si = cadd(y[i], dl[i]);
-                    cfma_nconj(t[k], a, y[i]);
-                    cfma_nconj(u[k], a, dl[i]);
-                    cfma_nconj(u[k], d, si);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            y[i] = cscale(t[i], inv);
-            if (i == l) y[i].x += 1.0;
-            dl[i] = cscale(u[i], inv);
-        }
-    }
-}
-
 // Fused pass over a unitary step matrix U (shared memory): cp = U^dagger c and gn = g U.
 // Each loaded element feeds two complex FMAs (the two separate passes were LSU-wavefront bound).
 template <int D, u64 CM = full_cmask<D>()>
@@ -396,8 +334,8 @@ __device__ __forceinline__ double redot(const cplx (&g)[D], const cplx (&t)[D]) 
 // Work item = (pulse, chunk of L steps).  Per step: A, then one Horner pass per first-order object
 // (variables, then error sources).  The chunk product q and the error aggregates wl live in shared
 // memory (private columns) so the Horner loops own the register file.
-template <int D, bool TRI>
-__global__ void __launch_bounds__(128, TRI ? 2 : 1)
+template <int D>
+__global__ void __launch_bounds__(128)
 k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
         cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb, int* __restrict__ status) {
     constexpr int G = GroupInfo<D>::G;
@@ -473,11 +411,6 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
 #pragma unroll
             for (int i = 0; i < D; ++i) mA[i + D * l] = cscale(mA[i + D * l], sc);
         }
-        cplx ta[TRI ? Tri<D>::n : 1];
-        if (TRI) {
-            __syncwarp(amask);
-            load_tri<D>(mA, reinterpret_cast<cplx(&)[Tri<D>::n]>(ta));
-        }
 
         // ---- first-order objects: variables then error sources (at least one pass, for U itself)
         for (int o = 0; o < max(nfo, 1); ++o) {
@@ -500,13 +433,7 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
             }
             __syncwarp(amask);
             cplx y[D], dl[D];
-            if (TRI) {
-                cplx td[TRI ? Tri<D>::n : 1];
-                load_tri<D>(mD, reinterpret_cast<cplx(&)[Tri<D>::n]>(td));
-                horner_fo_tri<D>(reinterpret_cast<cplx(&)[Tri<D>::n]>(ta), reinterpret_cast<cplx(&)[Tri<D>::n]>(td), l, m, y, dl);
-            } else {
-                horner_fo<D>(mA, mD, l, m, y, dl);
-            }
+            horner_fo<D>(mA, mD, l, m, y, dl);
             // squarings: Y <- Y Y ;  Dl <- Dl (Y + Dl) + Y Dl   (mX holds Y, mD is free after the Horner pass)
             for (int q2 = 0; q2 < sq; ++q2) {
                 __syncwarp(amask);
