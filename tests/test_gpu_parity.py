@@ -395,3 +395,39 @@ def test_non_hermitian_hamiltonian(gpu_ctx, N, t0, errors):
         assert np.abs(U[0] - Ur[0]).max() < 1e-12
         assert np.abs(U[1] - Ur[1]).max() < 2e-5 * np.abs(Ur[1]).max()
         assert np.abs(U[4] - Ur[4]).max() < 2e-4 * np.abs(Ur[4]).max()
+
+
+def test_no_gradient_mode_and_empty_batch(gpu_ctx):
+    """F / F_d2err only (no gradient sweeps, no mixed differences) agree with the full call; B = 0 is a no-op."""
+    fp = cz_problem(45, 2.2, ("amp", "freq"))
+    X = 2 * np.pi * np.random.default_rng(12).random((46, 5))
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    F_, Fdx_, F2_, F2dx_ = rg.calculate_fidelity_and_derivatives_batch(fp, X, want_grad=False)
+    assert Fdx_ is None and F2dx_ is None
+    assert np.array_equal(F, F_) and np.array_equal(F2, F2_)
+    from robustgrape_b200.unitary_calculations import device_problem
+    dp = device_problem(fp)
+    h, p = dp.handle_for(46)
+    assert dp.ctx.lib.rg_cost_and_grad_batch(h, 0, None, None, None, None) == 0
+
+
+def test_device_pointer_entry_point_matches_host_entry_point(gpu_ctx):
+    """rg_cost_and_grad_batch_dev (device buffers, caller's stream) == rg_cost_and_grad_batch (host buffers, pipelined slabs)."""
+    import torch
+    from robustgrape_b200.unitary_calculations import device_problem
+    fp = cz_problem(100, 7.613 / 10, ("amp",))
+    B, nx = 4100, 101                       # more than one host slab
+    X = 2 * np.pi * np.random.default_rng(13).random((B, nx))
+    cost_h, grad_h = rg.cost_and_gradient_batch(fp, X.T, [1e-4])
+    dp = device_problem(fp)
+    dX = torch.from_numpy(X).cuda()
+    dc = torch.empty(B, dtype=torch.float64, device="cuda")
+    dg = torch.empty(B * nx, dtype=torch.float64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        dp.ctx.set_stream(s.cuda_stream)
+        dp.cost_and_grad_batch_dev(B, nx, dX.data_ptr(), [1e-4], dc.data_ptr(), dg.data_ptr())
+        dp.ctx.synchronize()
+        dp.ctx.set_stream(0)
+    assert np.array_equal(dc.cpu().numpy(), cost_h)
+    assert np.array_equal(dg.cpu().numpy().reshape(B, nx).T, grad_h)
