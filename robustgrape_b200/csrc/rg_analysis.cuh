@@ -125,6 +125,78 @@ k_interaction_ops(const DevProblem P, const double* __restrict__ x, cplx* __rest
     }
 }
 
+
+// Time-parallel version for Hermitian problems: one group per chunk of L steps.  The forward state at the chunk start
+// comes from the chunk scan (Cb holds C at chunk *ends*), the step propagators from the workspace (object 0, dense
+// layout), and the error Hamiltonians are assembled on the fly:  O_k[e] = C_{k-1}^dagger (Herr_e(eps)/eps) C_{k-1}.
+template <int D>
+__global__ void __launch_bounds__(128)
+k_interaction_ops_par(const DevProblem P, const double* __restrict__ x, int L, int nc, const cplx* __restrict__ ws,
+                      const cplx* __restrict__ Cb, cplx* __restrict__ O) {
+    constexpr int G = GroupInfo<D>::G;
+    constexpr unsigned amask = GroupInfo<D>::amask;
+    constexpr int DD = D * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ cplx smem[];
+    const StagedDesc sd = stage_desc(P, reinterpret_cast<unsigned char*>(smem));
+    if (lane >= G * D) return;
+    const int g = lane / D, l = lane - g * D;
+    long long item = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * G + g;
+    const bool live = item < nc;
+    if (!live) item = nc - 1;
+    const int ch = (int)item;
+    const int nt = P.nterms;
+    cplx* base = smem + staged_desc_bytes(P.nterms, P.nent, D) / sizeof(cplx) + (size_t)(warp * G + g) * rg_odd(3 * DD + nt);
+    cplx* mC = base; cplx* mE = base + DD; cplx* mU = base + 2 * DD; cplx* coef = base + 3 * DD;
+    double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
+    for (int j = 0; j < P.a; ++j) xadd[j] = x[(size_t)P.p * P.N + j];
+    cplx c[D];
+    if (ch == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) c[i] = cmk(i == l ? 1.0 : 0.0, 0.0);
+    } else {
+        const cplx* src = Cb + (size_t)(ch - 1) * DD + l * D;
+#pragma unroll
+        for (int i = 0; i < D; ++i) c[i] = src[i];
+    }
+    const int k0 = ch * L, k1 = min(P.N, k0 + L);
+    for (int kk = 0; kk < L; ++kk) {
+        const bool ghost = (k0 + kk >= k1);
+        const int k = min(k0 + kk, k1 - 1);
+        for (int i = 0; i < P.p; ++i) xk[i] = x[(size_t)k * P.p + i];
+        __syncwarp(amask);
+#pragma unroll
+        for (int i = 0; i < D; ++i) { mC[i + D * l] = c[i]; mU[i + D * l] = ws[(size_t)k * DD + l * D + i]; }
+        __syncwarp(amask);
+        for (int e = 0; e < P.e; ++e) {
+            EvalCtx ec{xk, xadd, P.eps, P.table, P.N, k};
+            for (int t = l; t < nt; t += D) {
+                cplx b = cmk(0, 0), dl;
+                if (sd.terms[t].owner == e) term_coef(sd.terms[t], ec, RG_S_NONE, 0, 0.0, b, dl);
+                coef[t] = cscale(b, P.inv_eps);
+            }
+            __syncwarp(amask);
+            assemble_col<D>(sd.ents, sd.colptr, coef, mE, l);
+            __syncwarp(amask);
+            cplx t1[D], o[D];
+            matvec<D>(mE, c, t1);
+            matvec_adj<D>(mC, t1, o);
+            if (live && !ghost) {
+                cplx* dst = O + ((size_t)e * P.N + k) * DD + l * D;
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[i] = o[i];
+            }
+            __syncwarp(amask);
+        }
+        if (!ghost) {
+            cplx cn[D];
+            matvec<D>(mU, c, cn);
+#pragma unroll
+            for (int i = 0; i < D; ++i) c[i] = cn[i];
+        }
+    }
+}
+
 // Response function for one (frequency, error source) per block:
 //   S = sum_{j=0}^{N-1} e^{-i w dt j} O_{j+1} ,  T = sum_{k} e^{+i w dt (k - 1 + shift)} O_k   (k = 1..N)
 //   R = dt^2 [ Re tr_mod(T S P)/D - Re tr_mod(T P S P)/(D(D+1)) - Re(tr_mod(T P) tr_mod(S P))/(D(D+1)) ]

@@ -69,6 +69,7 @@ struct rg_problem {
     int force_dense = 0;      // RG_DENSE=1: treat H as dense (no structural-zero skipping)
     int force_group = 0;      // RG_GROUP=1: force the group-per-chunk k_steps kernel
     int force_group_sweeps = 0;   // RG_GROUP_SWEEPS=1: group (shared-memory) versions of k_chunk_agg / k_grad
+    int force_sequential_analysis = 0;   // RG_SEQ_ANALYSIS=1: time-sequential interaction-operator kernel
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
     double tri_density = 1.0;
@@ -466,12 +467,65 @@ static int materialize_impl(rg_problem* pr, const double* dx, cplx* dU, cplx* dU
 template <int D>
 static int launch_interaction(rg_problem* pr, const double* dx, cplx* dO) {
     rg_ctx* ctx = pr->ctx;
-    const DevProblem& P = pr->dp;
-    const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(6 * D * D + 2 * P.nterms) * sizeof(cplx);
-    int rc = set_smem(ctx, k_interaction_ops<D>, smem);
-    if (rc) return rc;
-    KTimer kt(ctx, RG_K_ANALYSIS);
-    k_interaction_ops<D><<<1, 32, smem, ctx->stream>>>(P, dx, dO, ctx->d_status);
+    DevProblem P = pr->dp;
+    constexpr int G = GroupInfo<D>::G;
+    const int DD = D * D;
+    const size_t cb = sizeof(cplx);
+    cudaStream_t st = ctx->stream;
+    if (!P.hermitian || P.N < 64 || pr->force_sequential_analysis) {
+        // time-sequential kernel: general (carries C^{-1} for non-Hermitian H), one warp
+        const size_t smem = staged_desc_bytes(P.nterms, P.nent, D) + (size_t)(6 * D * D + 2 * P.nterms) * sizeof(cplx);
+        int rc = set_smem(ctx, k_interaction_ops<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_ANALYSIS);
+        k_interaction_ops<D><<<1, 32, smem, st>>>(P, dx, dO, ctx->d_status);
+        return RG_OK;
+    }
+    // time-parallel path: step propagators -> chunk products -> prefix at chunk ends -> per-chunk forward sweep.
+    // Only U_k is needed: run the general step kernel on a copy of the problem without error sources / variables.
+    DevProblem Pu = P;
+    Pu.e = 0; Pu.nvar = 0; Pu.nstore = 1; Pu.wsm = DD; Pu.cmask = full_cmask<D>(); Pu.wsB = 1;
+    const int L = 16;
+    const int nc = (P.N + L - 1) / L;
+    if (pr->ws.ensure((size_t)P.N * DD * cb) || pr->Qb.ensure((size_t)nc * DD * cb) || pr->Wlb.ensure(16) ||
+        pr->Cb.ensure((size_t)nc * DD * cb) || pr->Wb.ensure(16) || pr->Gb.ensure((size_t)nc * DD * cb) ||
+        pr->G1b.ensure(16) || pr->H1b.ensure(16) || pr->dM.ensure((size_t)DD * cb))
+        RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed");
+    {
+        const int gs = k1_group_stride(D, P.nterms, 0);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_steps<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_STEPS);
+        k_steps<D><<<(nc + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(Pu, dx, 1, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(),
+                                                                        pr->Wlb.as<cplx>(), ctx->d_status);
+    }
+    {
+        const int gs = k2_group_stride(D);
+        const size_t smem = (size_t)G * gs * cb;
+        int rc = set_smem(ctx, k_scan<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_SCAN);
+        k_scan<D><<<dim3(1, 1), 32, smem, st>>>(Pu, dx, 1, nc, pr->Qb.as<cplx>(), pr->Wlb.as<cplx>(), pr->Cb.as<cplx>(),
+                                              pr->Wb.as<cplx>(), pr->Gb.as<cplx>(), pr->G1b.as<cplx>(), pr->H1b.as<cplx>(),
+                                              nullptr, nullptr, nullptr, 1, pr->dM.as<cplx>(), nullptr);
+    }
+    {
+        const int gs = rg_odd(3 * DD + P.nterms);
+        const size_t dbytes = staged_desc_bytes(P.nterms, P.nent, D);
+        int wpc = 4;
+        while (wpc > 1 && (size_t)wpc * G * gs * cb + dbytes > 200 * 1024) wpc >>= 1;
+        const size_t smem = (size_t)wpc * G * gs * cb + dbytes;
+        int rc = set_smem(ctx, k_interaction_ops_par<D>, smem);
+        if (rc) return rc;
+        KTimer kt(ctx, RG_K_ANALYSIS);
+        k_interaction_ops_par<D><<<(nc + wpc * G - 1) / (wpc * G), wpc * 32, smem, st>>>(P, dx, L, nc, pr->ws.as<cplx>(),
+                                                                                      pr->Cb.as<cplx>(), dO);
+    }
+    CU(ctx, cudaGetLastError());
     return RG_OK;
 }
 template <int D>

@@ -200,10 +200,12 @@ def _analysis_case(model="symmetric_blockaded", N=60):
     return fp, x
 
 
-@pytest.mark.parametrize("model", ["symmetric_blockaded", "full_blockaded"])
-def test_interaction_error_operators(gpu_ctx, model):
-    """reference src/UnitaryCalculations.jl:180-204; well-conditioned (no finite difference): 1e-11 relative."""
-    fp, x = _analysis_case(model)
+@pytest.mark.parametrize("model,N", [("symmetric_blockaded", 60), ("full_blockaded", 60), ("symmetric_blockaded", 203),
+                                     ("full_blockaded", 130)])
+def test_interaction_error_operators(gpu_ctx, model, N):
+    """reference src/UnitaryCalculations.jl:180-204; well-conditioned (no finite difference): 1e-11 relative.
+    N < 64 runs the time-sequential kernel, larger N the time-parallel chunk pipeline."""
+    fp, x = _analysis_case(model, N)
     got = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
     ref = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
     assert got.shape == ref.shape
