@@ -6,8 +6,12 @@
 
 One "step" = one cost+gradient evaluation (reference `calculate_common!`, src/FidelityCalculations.jl:174-184,
 without host regularisation) of every pulse of the batch: 8192 random-init pulses x 1000 time steps of the
-5-level symmetric-blockaded Rydberg CZ problem (examples/time_optimal_cz.jl), sharded over the ranks
-(strong scaling: the batch is fixed), followed for N > 1 by one NCCL all-gather of [cost | grad].
+5-level symmetric-blockaded Rydberg CZ problem (examples/time_optimal_cz.jl) per GPU. Pulses are independent, so for
+N > 1 they are sharded over the ranks with no collective inside an evaluation; each step ends with an all-gather of every
+rank's [cost | grad] block (peer-memory copies by default, `--gather nccl` for ncclAllGather).
+`--scaling weak` (default): the multi-start batch grows with the box, 8192 pulses per GPU.
+`--scaling strong`: the 8192-pulse batch is fixed and split over the ranks (also measured and reported under
+`extra.strong_scaling` when N > 1).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -145,8 +149,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "GRAPE cost+grad evals/sec (CZ, batched pulses)", "value": val, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
+        "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, max(1, args.gpus), args.scaling, "none"),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} pulses of the workload per step (C++ port of the reference's literal "
                                    "algorithm; Julia unavailable in this image)"},
@@ -155,12 +159,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
+def workload_config(args, world=1, scaling="weak", gather="peer"):
+    per_gpu = args.batch if scaling == "weak" else args.batch // world
+    how = {"peer": "all-gather of [cost|grad] per step by peer-memory copies (CUDA IPC mappings, copy engines over NVLink)",
+           "nccl": "NCCL all-gather of [cost|grad] per step", "none": "no gather (diagnostic)"}[gather]
     return {
         "workload": f"C4 multi-start CZ: {args.batch} random-init pulses x {args.ntimes} time steps, d=5 symmetric-blockaded "
-                    f"Rydberg, p=1, a=1, e={args.nerr}, t0={T0}, eps=1e-8, eps2=1e-4 (examples/time_optimal_cz.jl)",
-        "batch": args.batch, "ntimes": args.ntimes, "nerr": args.nerr,
-        "sharding": "pulses over ranks; NCCL all-gather of [cost|grad] per step, overlapped with the next step's kernels (double-buffered)",
+                    f"Rydberg, p=1, a=1, e={args.nerr}, t0={T0}, eps=1e-8, eps2=1e-4 (examples/time_optimal_cz.jl)"
+                    + (f"; {scaling} scaling: {per_gpu} pulses per GPU, {per_gpu * world} in total" if world > 1 else ""),
+        "batch": per_gpu * world, "per_gpu_batch": per_gpu, "ntimes": args.ntimes, "nerr": args.nerr,
+        "sharding": f"independent pulses over ranks, no collective inside an evaluation; {how}, overlapped with the next "
+                    "step's kernels (double-buffered)" if world > 1 else "single GPU",
         "l2": "each step streams the step-matrix workspace (0.26 MB/pulse written then read twice, 2.1 GB per 8192-pulse batch) -- far larger than the 126 MB L2; no explicit flush",
     }
 
@@ -177,6 +186,10 @@ def main():
     ap.add_argument("--cpu-pulses-per-thread", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --batch pulses per GPU (default), strong = --batch pulses in total")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
+                    help="N > 1: how the per-rank [cost|grad] blocks are gathered each step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -200,13 +213,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    B, N = args.batch, args.ntimes
+    N = args.ntimes
     nx = N + 1
-    assert B % world == 0, "batch must divide over the ranks"
-    Bs = B // world
-    Xall = make_pulses(N, B)
-    Xs = np.ascontiguousarray(Xall[rank * Bs:(rank + 1) * Bs])
     coeff = [1e-4] * args.nerr
+    gather = args.gather if world > 1 else "none"
+    if os.environ.get("RG_BENCH_NO_GATHER"):
+        gather = "none"
+    gather_mode = int(os.environ.get("RG_GATHER_MODE", "0"))        # 0 copy engines, 1 store kernel
 
     ctx = Context(local)
     # All work (library kernels, NCCL, timing events) goes on one non-default torch stream.
@@ -216,64 +229,118 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     prob = Problem(make_problem(N, args.nerr), ctx)
 
-    dX = torch.from_numpy(Xs).to(dev)                              # inputs resident in HBM
-    # [cost (Bs) | grad (Bs, nx)] per rank; two buffers so that the all-gather of step i (NCCL's own stream) overlaps the
-    # kernels of step i+1: in multi-start optimisation a rank's next evaluation only needs its own shard's gradients.
-    out_locals = [torch.empty(Bs * (1 + nx), dtype=torch.float64, device=dev) for _ in range(2)]
-    out_alls = [torch.empty(world * Bs * (1 + nx), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else out_locals
-    out_local = out_locals[0]
-    dcost, dgrad = out_local[:Bs], out_local[Bs:]
-    pending = [None, None]
-    step_no = [0]
-
-    def step():
-        i = step_no[0] & 1
-        step_no[0] += 1
-        if pending[i] is not None:
-            pending[i].wait()                                      # buffer i is free again (its all-gather finished)
-            pending[i] = None
-        ol = out_locals[i]
-        prob.cost_and_grad_batch_dev(Bs, nx, dX.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr())
-        if world > 1 and not os.environ.get("RG_BENCH_NO_GATHER"):      # (diagnostic switch: compute-only scaling)
-            pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
-
-    def drain():
-        for i in (0, 1):
-            if pending[i] is not None:
-                pending[i].wait()
-                pending[i] = None
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def shard_inputs(scaling):
+        """(global batch, per-rank batch, this rank's pulses)."""
+        if scaling == "weak" or world == 1:
+            return args.batch * world, args.batch, make_pulses(N, args.batch, seed=43 + rank)
+        assert args.batch % world == 0, "batch must divide over the ranks"
+        bs = args.batch // world
+        return args.batch, bs, np.ascontiguousarray(make_pulses(N, args.batch)[rank * bs:(rank + 1) * bs])
+
+    def device_run(scaling, steps, warmup, sample_clocks):
+        """Times `steps` evaluations of this rank's shard, inputs resident in HBM; max over ranks."""
+        B, Bs, Xs = shard_inputs(scaling)
+        dX = torch.from_numpy(Xs).to(dev)
+        blk = Bs * (1 + nx)
+        # [cost (Bs) | grad (Bs, nx)] per rank; two buffers so that the gather of step i (side streams / NCCL's stream)
+        # overlaps the kernels of step i+1: in multi-start optimisation a rank's next evaluation only needs its own shard.
+        out_locals = [torch.empty(blk, dtype=torch.float64, device=dev) for _ in range(2)]
+        pg = None
+        out_alls = None
+        if gather == "peer":
+            from robustgrape_b200.sharding import PeerGather
+            pg = PeerGather(ctx, rank, world, blk, nbuf=2, mode=gather_mode)
+            out_alls = [pg.view(i, dev) for i in range(2)]
+        elif gather == "nccl":
+            out_alls = [torch.empty(world * blk, dtype=torch.float64, device=dev) for _ in range(2)]
+        pending = [None, None]
+        step_no = [0]
+
+        def step():
+            i = step_no[0] & 1
+            step_no[0] += 1
+            if pending[i] is not None:
+                pending[i].wait()                                  # buffer i is free again (its gather finished)
+                pending[i] = None
+            if pg is not None:
+                pg.wait(i)
+            ol = out_locals[i]
+            prob.cost_and_grad_batch_dev(Bs, nx, dX.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr())
+            if gather == "nccl":
+                pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
+            elif pg is not None:
+                pg.push(ol.data_ptr(), i)
+
+        def drain():
+            for i in (0, 1):
+                if pending[i] is not None:
+                    pending[i].wait()
+                    pending[i] = None
+                if pg is not None:
+                    pg.wait(i)
+
+        for _ in range(warmup):
+            step()
+        drain()
+        ctx.synchronize()
+        barrier()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        e0.record()
+        for _ in range(steps):
+            step()
+        drain()                                                    # every step's gather completes inside the timed region
+        e1.record()
+        barrier()
+        if sampler:
+            sampler.__exit__(None, None, None)
+        launches = ctx.launch_count - l0
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ctx.synchronize()
+        last = (step_no[0] - 1) & 1
+        if out_alls is not None:
+            # the gathered buffer must hold every rank's block: check against one untimed NCCL all-gather
+            ref = torch.empty(world * blk, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(ref, out_locals[last])
+            torch.cuda.synchronize()
+            assert torch.equal(ref, out_alls[last]), f"rank {rank}: gathered [cost|grad] differs from NCCL all-gather"
+            del ref
+        cost_host = out_locals[last][:Bs].cpu().numpy()
+        if pg is not None:
+            barrier()
+            out_alls = None
+            pg.close(barrier)
+        return {"B": B, "Bs": Bs, "Xs": Xs, "dX": dX, "ms": float(ms.item()), "launches": launches, "cost": cost_host,
+                "clocks": sampler.summary() if sampler else None, "out": out_locals[0]}
+
     peak_dfma = peak_dmma = None
     if rank == 0:
         peak_dfma, peak_dmma = ctx.measure_fp64_peak(0.3)
 
-    for _ in range(args.warmup):
-        step()
-    drain()
-    ctx.synchronize()
-    barrier()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        drain()                                                    # every step's all-gather completes inside the timed region
-        e1.record()
-        barrier()
-    launches = ctx.launch_count - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    scaling = args.scaling if world > 1 else "weak"
+    run = device_run(scaling, args.steps, args.warmup, True)
+    B, Bs, Xs, dX = run["B"], run["Bs"], run["Xs"], run["dX"]
+    ms_total, launches, cost_host = run["ms"], run["launches"], run["cost"]
     value = B * args.steps / (ms_total * 1e-3)
-    ctx.synchronize()
-    cost_host = out_locals[(step_no[0] - 1) & 1][:Bs].cpu().numpy()
+    dcost, dgrad = run["out"][:Bs], run["out"][Bs:]
+    other = None
+    if world > 1 and not args.no_extra:
+        oscal = "strong" if scaling == "weak" else "weak"
+        if oscal == "weak" or args.batch % world == 0:
+            o = device_run(oscal, args.steps, args.warmup, False)
+            other = {"scaling": oscal, "batch": o["B"], "per_gpu_batch": o["Bs"], "ms_per_step": o["ms"] / args.steps,
+                     "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3)}
+            del o
 
     # ---- e2e: host buffers through the C ABI, H2D and D2H inside the timed region
     hX = torch.from_numpy(Xs).pin_memory()
@@ -399,13 +466,16 @@ def main():
         line = {
             "metric": "GRAPE cost+grad evals/sec (CZ, batched pulses)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
-            "clocks": clk.summary(),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world, scaling, gather),
+            "clocks": run["clocks"],
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": B * nx * 8, "d2h_bytes_per_step": B * (nx + 1) * 8},
             "gpu_launches": launches * world,
             "roofline": roof,
         }
+        if other:
+            extra = dict(extra or {})
+            extra[other["scaling"] + "_scaling"] = other
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
@@ -414,7 +484,7 @@ def main():
             sample = min(B, max(8, args.cpu_pulses_per_thread * threads))
             pp = cpu_port.PortProblem(make_problem(N, args.nerr))
             t = time.perf_counter()
-            c_cpu, g_cpu = pp.cost_and_grad_batch(Xall[:sample].T, coeff, threads)
+            c_cpu, g_cpu = pp.cost_and_grad_batch(Xs[:sample].T, coeff, threads)
             dt = time.perf_counter() - t
             line["cpu_baseline"] = {"value": sample / dt, "unit": "evals/s", "cores": threads, "kind": "port",
                                     "sample": f"first {sample} pulses of the workload, C++ port of the reference's literal "

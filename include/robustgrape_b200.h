@@ -149,6 +149,27 @@ int rg_expectation_values(rg_problem* prob, const double* x, double* out);
 int rg_host_alloc(void** ptr, uint64_t bytes);
 void rg_host_free(void* ptr);
 
+/* --- Gather of per-shard results through peer memory (one process per GPU, one NVLink/NVSwitch node) --------------
+ * The reference is a single CPU process and has no counterpart; this is north_star's "allgather of per-shard costs and
+ * gradients" for the multi-start batch, written so that it never competes with the evaluation kernels for SMs.
+ *   rg_peer_buffer_create : cudaMalloc a buffer on the context device and export its 64-byte CUDA IPC handle.
+ *   rg_peer_buffer_open   : map another process's buffer (handle obtained out of band) into this process.
+ *   rg_gather_to_peers    : copy src[0, bytes) to peer_base[p] + dst_offset for p < npeers (a base may be the caller's
+ *                           own buffer). Ordered after everything queued on the context stream so far; runs on the
+ *                           library's side streams, i.e. asynchronously to later work on the context stream.
+ *                           mode 0: copy engines (one cudaMemcpyAsync per peer); mode 1: one kernel storing to all peers.
+ *                           slot (0/1) names the completion event, for double-buffered sources.
+ *   rg_gather_wait        : the context stream waits (on the device) for the gather last issued on `slot`.
+ * rg_ctx_synchronize() also waits for outstanding gathers. Cross-process completion (all peers have written into my
+ * buffer) is the caller's barrier.                                                                                  */
+int rg_peer_buffer_create(rg_ctx* ctx, uint64_t bytes, void** dptr, unsigned char handle[64]);
+int rg_peer_buffer_open(rg_ctx* ctx, const unsigned char handle[64], void** dptr);
+int rg_peer_buffer_close(rg_ctx* ctx, void* dptr);
+int rg_peer_buffer_destroy(rg_ctx* ctx, void* dptr);
+int rg_gather_to_peers(rg_ctx* ctx, const void* src, uint64_t bytes, int32_t npeers, void* const* peer_base,
+                       uint64_t dst_offset, int32_t slot, int32_t mode);
+int rg_gather_wait(rg_ctx* ctx, int32_t slot);
+
 /* FP64 peak microbenchmarks (DFMA loop, DMMA m8n8k4 loop) on the context device: TFLOP/s. */
 int rg_measure_fp64_peak(rg_ctx* ctx, double seconds, double* dfma_tflops, double* dmma_tflops);
 

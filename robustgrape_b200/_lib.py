@@ -73,6 +73,12 @@ SIGNATURES = {
     "rg_expectation_values": (C.c_int, [_vp, _vp, _vp]),
     "rg_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "rg_host_free": (None, [_vp]),
+    "rg_peer_buffer_create": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp), C.c_char_p]),
+    "rg_peer_buffer_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "rg_peer_buffer_close": (C.c_int, [_vp, _vp]),
+    "rg_peer_buffer_destroy": (C.c_int, [_vp, _vp]),
+    "rg_gather_to_peers": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32, C.POINTER(_vp), C.c_uint64, C.c_int32, C.c_int32]),
+    "rg_gather_wait": (C.c_int, [_vp, C.c_int32]),
     "rg_measure_fp64_peak": (C.c_int, [_vp, C.c_double, _dp, _dp]),
 }
 
@@ -144,6 +150,33 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self.check(self.lib.rg_measure_fp64_peak(self.handle, float(seconds), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # ---- peer-memory gather (include/robustgrape_b200.h: rg_peer_buffer_*, rg_gather_to_peers)
+    def peer_buffer_create(self, nbytes):
+        """cudaMalloc `nbytes` on this device; returns (device pointer, 64-byte IPC handle)."""
+        p = _vp()
+        h = C.create_string_buffer(64)
+        self.check(self.lib.rg_peer_buffer_create(self.handle, int(nbytes), C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_buffer_open(self, handle):
+        p = _vp()
+        self.check(self.lib.rg_peer_buffer_open(self.handle, bytes(handle), C.byref(p)))
+        return p.value
+
+    def peer_buffer_close(self, ptr):
+        self.check(self.lib.rg_peer_buffer_close(self.handle, _vp(ptr)))
+
+    def peer_buffer_destroy(self, ptr):
+        self.check(self.lib.rg_peer_buffer_destroy(self.handle, _vp(ptr)))
+
+    def gather_to_peers(self, src_ptr, nbytes, peer_ptrs, dst_offset, slot=0, mode=0):
+        arr = (_vp * len(peer_ptrs))(*[_vp(p) for p in peer_ptrs])
+        self.check(self.lib.rg_gather_to_peers(self.handle, _vp(src_ptr), int(nbytes), len(peer_ptrs), arr, int(dst_offset),
+                                               int(slot), int(mode)))
+
+    def gather_wait(self, slot=0):
+        self.check(self.lib.rg_gather_wait(self.handle, int(slot)))
 
     def close(self):
         if getattr(self, "handle", None):

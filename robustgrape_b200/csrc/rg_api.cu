@@ -56,6 +56,12 @@ extern "C" void rg_ctx_destroy(rg_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (int i = 0; i < 2; i++) {
+        if (c->s_peer[i]) cudaStreamDestroy(c->s_peer[i]);
+        if (c->ev_gather[i]) cudaEventDestroy(c->ev_gather[i]);
+    }
+    if (c->ev_src) cudaEventDestroy(c->ev_src);
+    if (c->ev_peer_join) cudaEventDestroy(c->ev_peer_join);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     delete c;
@@ -74,6 +80,8 @@ extern "C" int rg_ctx_synchronize(rg_ctx* c) {
     if (!c) return RG_ERR_INVALID;
     CU(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; i++)
+        if (c->gather_pending[i]) { CU(c, cudaEventSynchronize(c->ev_gather[i])); c->gather_pending[i] = false; }
     if (*c->h_status != 0) {
         const int fl = *c->h_status;
         *c->h_status = 0;
@@ -464,3 +472,4 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
 }
 
 #include "rg_api_analysis.inl"
+#include "rg_peer.inl"

@@ -27,6 +27,9 @@ struct rg_ctx {
     // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
     int host_slabs = 4;                               // RG_HOST_SLABS (upper bound; slabs hold >= 2048 pulses)
+    cudaStream_t s_peer[2] = {nullptr, nullptr};      // side streams of rg_gather_to_peers (created on first use)
+    cudaEvent_t ev_src = nullptr, ev_peer_join = nullptr, ev_gather[2] = {nullptr, nullptr};
+    bool gather_pending[2] = {false, false};
     bool timing = false;
     struct Span { int kernel; cudaEvent_t e0, e1; };
     std::vector<Span> spans;

@@ -433,3 +433,29 @@ def test_device_pointer_entry_point_matches_host_entry_point(gpu_ctx):
         dp.ctx.set_stream(0)
     assert np.array_equal(dc.cpu().numpy(), cost_h)
     assert np.array_equal(dg.cpu().numpy().reshape(B, nx).T, grad_h)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_peer_gather_single_process(gpu_ctx, mode):
+    """rg_gather_to_peers (include/robustgrape_b200.h): with one process the only 'peer' is the rank's own buffer; the block
+    must land at its slot, ordered after the work queued on the context stream. (The multi-process path is checked against
+    an NCCL all-gather inside bench.py whenever it runs on more than one GPU.)"""
+    import torch
+    from robustgrape_b200.sharding import PeerGather
+    world, rank, blk = 4, 2, 1003                         # odd block: exercises the 8-byte path of the store kernel
+    pg = PeerGather(gpu_ctx, 0, 1, world * blk, nbuf=2, mode=mode, exchange=lambda h: [h])
+    pg.rank, pg.world, pg.block = rank, world, blk        # view the one buffer as 4 slots, act as rank 2
+    dev = torch.device("cuda", gpu_ctx.device)
+    for buf in (0, 1):
+        out = pg.view(buf, dev)
+        out.zero_()
+        src = torch.arange(blk, dtype=torch.float64, device=dev) + 7.0 * buf
+        torch.cuda.synchronize()
+        pg.push(src.data_ptr(), buf)
+        pg.wait(buf)
+        gpu_ctx.synchronize()
+        got = out.cpu().numpy().reshape(world, blk)
+        assert np.array_equal(got[rank], src.cpu().numpy())
+        assert not got[[0, 1, 3]].any()
+    del out
+    pg.close()
