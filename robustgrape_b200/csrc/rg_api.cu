@@ -263,6 +263,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_DENSE")) pr->force_dense = atoi(s);
     if (const char* s = getenv("RG_GROUP")) pr->force_group = atoi(s);
     if (const char* s = getenv("RG_GROUP_SWEEPS")) pr->force_group_sweeps = atoi(s);
+    if (const char* s = getenv("RG_FUSED_AGG")) pr->fused_agg = atoi(s);
     if (const char* s = getenv("RG_SEQ_ANALYSIS")) pr->force_sequential_analysis = atoi(s);
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
     if (P.hermitian && d <= 5 && P.nterms <= RG_T_MAX_TERMS) {

@@ -52,6 +52,14 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return cmk(a.x * b.x - a.
 __device__ __forceinline__ cplx cscale(cplx a, double s) { return cmk(a.x * s, a.y * s); }
 __device__ __forceinline__ cplx cconj(cplx a) { return cmk(a.x, -a.y); }
 // acc += a*b  (4 DFMA)
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): two complex doubles per instruction; p must be 32-byte aligned.
+// Halves the L1 tag look-ups of the thread-per-chunk sweeps, whose lanes each stream their own 128-byte lines.
+__device__ __forceinline__ void ld256(const cplx* __restrict__ p, cplx& a, cplx& b) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st256(cplx* __restrict__ p, const cplx a, const cplx b) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
 __device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {
     acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
     acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);

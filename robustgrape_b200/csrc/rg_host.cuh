@@ -71,6 +71,8 @@ struct rg_problem {
     int chunk_override = 0;
     int force_dense = 0;      // RG_DENSE=1: treat H as dense (no structural-zero skipping)
     int force_group = 0;      // RG_GROUP=1: force the group-per-chunk k_steps kernel
+    int fused_agg = 0;            // RG_FUSED_AGG=1: form the e = 0 chunk aggregates inside k_steps_t (measured slower: the tree
+                                  // product issues 5 x 64 DFMA warp-instructions with most lanes idle)
     int force_group_sweeps = 0;   // RG_GROUP_SWEEPS=1: group (shared-memory) versions of k_chunk_agg / k_grad
     int force_sequential_analysis = 0;   // RG_SEQ_ANALYSIS=1: time-sequential interaction-operator kernel
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
@@ -223,17 +225,25 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         // Hermitian fast path: one thread per time step, triangles in registers; aggregates in a second kernel.
         constexpr int DT = kThreadOK ? D : 2;
         constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
-        const size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
-        const long long items = (long long)B * P.N;
+        size_t smem = staged_plan_bytes(P.nterms, pr->tri.nent, D);
+        // opt-in (RG_FUSED_AGG=1): e = 0, sparse pattern, power-of-two chunk length -> chunk aggregates formed inside k_steps_t
+        const bool fuse_agg = kSparseThread && ne == 0 && !pr->force_group_sweeps && pr->fused_agg && L <= 32 && (L & (L - 1)) == 0;
+        const int agg_off = (int)smem;
+        if (fuse_agg) smem += (size_t)128 * WSM * cb;
+        const long long items = (long long)B * (fuse_agg ? (long long)nc * L : (long long)P.N);
         const int grid = (int)((items + 127) / 128);
         {
             KTimer kt(ctx, RG_K_STEPS);
-            k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
+            if (fuse_agg)
+                k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status, L, nc,
+                                                           pr->Qb.as<cplx>(), agg_off);
+            else
+                k_steps_t<DT, UM><<<grid, 128, smem, st>>>(P, pr->tri, dX, B, pr->ws.as<cplx>(), ctx->d_status);
         }
         const long long citems = (long long)B * nc;
-        bool agg_done = false;
+        bool agg_done = fuse_agg;
         if constexpr (kSparseThread) {
-            if (!pr->force_group_sweeps) {
+            if (!agg_done && !pr->force_group_sweeps) {
                 // sparse pattern: whole matrices in one thread's registers, no shared memory
                 KTimer kt(ctx, RG_K_AGG);
                 k_chunk_agg_t<D, CMS><<<(int)((citems + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Qb.as<cplx>(), pr->Wlb.as<cplx>());

@@ -111,40 +111,160 @@ __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], cons
     }
 }
 
+// Column l of a compact (pattern) matrix to global memory. With an even number of stored elements every matrix starts on
+// a 32-byte boundary, so two consecutive stored elements of the column whose first compact index is even go out as one
+// STG.256.
+template <int D, u64 CMS>
+__host__ __device__ constexpr int pat_next_row(int i, int l) {          // next stored row after i in column l (D if none)
+    for (int r = i + 1; r < D; ++r)
+        if (Pat<D, CMS>::has(r, l)) return r;
+    return D;
+}
+template <int D, u64 CMS>
+__host__ __device__ constexpr int pat_prev_row(int i, int l) {          // previous stored row before i in column l (-1 if none)
+    for (int r = i - 1; r >= 0; --r)
+        if (Pat<D, CMS>::has(r, l)) return r;
+    return -1;
+}
+template <int D, u64 CMS, int l>
+__device__ __forceinline__ void store_col(cplx* __restrict__ dst, const cplx (&v)[D]) {
+    typedef Pat<D, CMS> PT;
+    constexpr bool PAIRS = (PT::nnz & 1) == 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        if (!PT::has(i, l)) continue;
+        const int prev = pat_prev_row<D, CMS>(i, l), next = pat_next_row<D, CMS>(i, l);
+        // pairs are formed greedily from the top of the column: element i is the second of a pair iff the element before
+        // it has an even compact index (the compact indices of a column are consecutive)
+        const bool second = PAIRS && prev >= 0 && (PT::idx(prev, l) & 1) == 0;
+        if (second) continue;
+        const bool first = PAIRS && next < D && (PT::idx(i, l) & 1) == 0;
+        if (first) st256(dst + PT::idx(i, l), v[i], v[next < D ? next : i]);
+        else dst[PT::idx(i, l)] = v[i];
+    }
+}
+
 template <int D, unsigned UMASK, int l>
 __device__ __forceinline__ void columns(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD, int m,
-                                        bool live, cplx* __restrict__ dstD, cplx* __restrict__ dstU) {
+                                        bool live, cplx* __restrict__ dstD, cplx* __restrict__ dstU, cplx* smU = nullptr) {
     typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     if constexpr (l < D) {
         if constexpr (PT::has(l, l)) {              // inert levels: U(l,l) = 1, dU = 0, nothing computed or stored
             cplx y[D], dl[D];
             horner_col_tri<D, UMASK, l>(ta, td, mA, mD, m, y, dl);
-            if (live) {
+            if (smU) {                              // fused chunk aggregate: U of this step, element-major in shared memory
 #pragma unroll
                 for (int i = 0; i < D; ++i)
-                    if (PT::has(i, l)) {
-                        if (dstD) dstD[PT::idx(i, l)] = dl[i];
-                        if (dstU) dstU[PT::idx(i, l)] = y[i];
-                    }
+                    if (PT::has(i, l)) smU[PT::idx(i, l) * 128] = live ? y[i] : cmk(i == l ? 1.0 : 0.0, 0.0);
+            }
+            if (live) {
+                if (dstD) store_col<D, stored_from_tri(D, UMASK), l>(dstD, dl);
+                if (dstU) store_col<D, stored_from_tri(D, UMASK), l>(dstU, y);
             }
         }
-        columns<D, UMASK, l + 1>(ta, td, mA, mD, m, live, dstD, dstU);
+        columns<D, UMASK, l + 1>(ta, td, mA, mD, m, live, dstD, dstU, smU);
     }
+}
+
+// ---- matrices restricted to a compile-time pattern (used by the thread-per-chunk sweeps and the fused aggregate)
+template <int D, u64 CM>
+struct PMat {                       // matrix restricted to the pattern, stored compactly
+    cplx v[Pat<D, CM>::nnz];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = cmk(0.0, 0.0);
+    }
+    __device__ __forceinline__ void identity() {
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (Pat<D, CM>::has(i, j)) v[Pat<D, CM>::idx(i, j)] = cmk(i == j ? 1.0 : 0.0, 0.0);
+    }
+    __device__ __forceinline__ void load(const cplx* __restrict__ p) {
+        if constexpr ((Pat<D, CM>::nnz & 1) == 0) {        // matrices start on 32-byte boundaries: 256-bit loads
+#pragma unroll
+            for (int i = 0; i < Pat<D, CM>::nnz; i += 2) ld256(p + i, v[i], v[i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = p[i];
+        }
+    }
+};
+// dense d x d (column-major) <-> pattern
+template <int D, u64 CM>
+__device__ __forceinline__ void pmat_from_dense(PMat<D, CM>& m, const cplx* __restrict__ p) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (Pat<D, CM>::has(i, j)) m.v[Pat<D, CM>::idx(i, j)] = p[i + D * j];
+}
+// unit_inert: entries (l,l) of inert levels (diagonal bit absent) are written as 1 (products of propagators), else 0
+template <int D, u64 CM>
+__device__ __forceinline__ void pmat_to_dense(const PMat<D, CM>& m, cplx* __restrict__ p, bool unit_inert) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            p[i + D * j] = Pat<D, CM>::has(i, j) ? m.v[Pat<D, CM>::idx(i, j)] : cmk((i == j && unit_inert) ? 1.0 : 0.0, 0.0);
+}
+// C = op(A) B with op = none (ADJ = false) or conjugate transpose (ADJ = true); the closure pattern is closed under
+// products and adjoints, so the result stays inside it.
+template <int D, u64 CM, bool ADJ, bool ACC>
+__device__ __forceinline__ void pmat_mul(PMat<D, CM>& c, const PMat<D, CM>& a, const PMat<D, CM>& b) {
+    typedef Pat<D, CM> PT;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (!PT::has(i, j)) continue;
+            cplx acc = ACC ? c.v[PT::idx(i, j)] : cmk(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                if (!PT::has(k, j)) continue;
+                if (ADJ) { if (PT::has(k, i)) cfma_conj(acc, a.v[PT::idx(k, i)], b.v[PT::idx(k, j)]); }
+                else { if (PT::has(i, k)) cfma(acc, a.v[PT::idx(i, k)], b.v[PT::idx(k, j)]); }
+            }
+            c.v[PT::idx(i, j)] = acc;
+        }
+}
+// Re tr(A B)
+template <int D, u64 CM>
+__device__ __forceinline__ double pmat_retrace(const PMat<D, CM>& a, const PMat<D, CM>& b) {
+    typedef Pat<D, CM> PT;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (PT::has(i, j) && PT::has(j, i)) {
+                const cplx x = a.v[PT::idx(i, j)], y = b.v[PT::idx(j, i)];
+                s = fma(x.x, y.x, s); s = fma(-x.y, y.y, s);
+            }
+    return s;
 }
 
 template <int D, unsigned UMASK>
 __global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 4)
 k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
-          int* __restrict__ status) {
+          int* __restrict__ status, int aggL = 0, int nc = 0, cplx* __restrict__ Qb = nullptr, int agg_off = 0) {
+    // aggL > 0 (a power of two <= 32, no error sources): the time axis is padded to nc*aggL so that every aligned group of
+    // aggL lanes is one chunk of one pulse, and the chunk aggregate Q = U_last ... U_first is formed here by a tree product in
+    // shared memory instead of re-reading the step matrices in k_chunk_agg_t.
     constexpr int NP = Tri<D>::n;
     typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
     const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
-    const long long total = (long long)B * P.N;
+    const int Np = aggL ? nc * aggL : P.N;                       // padded steps per pulse
+    const long long total = (long long)B * Np;
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = item < total;
-    if (!live) item = total - 1;
-    const int b = (int)(item / P.N), k = (int)(item % P.N);
+    const bool in_grid = item < total;
+    if (!in_grid) item = total - 1;
+    const int b = (int)(item / Np), kp = (int)(item % Np);
+    const bool live = in_grid && kp < P.N;
+    const int k = min(kp, P.N - 1);
+    cplx* smU = aggL ? reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(smem) + agg_off) + threadIdx.x : nullptr;
     const double* xp = X + (size_t)b * P.nx;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
@@ -208,7 +328,30 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
         const unsigned mD = (nfo == 0) ? 0u : (o < nv ? tp.maskVar[o] : tp.maskErr[o - nv]);
         // ---- columns (unrolled: the pattern of each column is known at compile time)
         columns<D, UMASK, 0>(ta, td, tp.maskA, mD, m, live, nfo > 0 ? wsk + (size_t)(1 + o) * objS : nullptr,
-                             o == 0 ? wsk : nullptr);
+                             o == 0 ? wsk : nullptr, o == 0 ? smU : nullptr);
+    }
+    if constexpr (PT::nnz <= 12) if (aggL) {
+        // tree product over the aggL lanes of a chunk: after level s lane t (t % 2s == 0) holds U_{t+2s-1} ... U_t
+        typedef PMat<D, stored_from_tri(D, UMASK)> M;
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        for (int s = 1; s < aggL; s <<= 1) {
+            if ((lane & (2 * s - 1)) == 0) {
+                M lo, hi, pr;
+#pragma unroll
+                for (int i = 0; i < PT::nnz; ++i) { lo.v[i] = smU[i * 128]; hi.v[i] = smU[i * 128 + s]; }
+                pmat_mul<D, stored_from_tri(D, UMASK), false, false>(pr, hi, lo);
+#pragma unroll
+                for (int i = 0; i < PT::nnz; ++i) smU[i * 128] = pr.v[i];
+            }
+            __syncwarp();
+        }
+        if ((lane & (aggL - 1)) == 0 && in_grid) {
+            M q;
+#pragma unroll
+            for (int i = 0; i < PT::nnz; ++i) q.v[i] = smU[i * 128];
+            pmat_to_dense<D, stored_from_tri(D, UMASK)>(q, Qb + ((size_t)b * nc + kp / aggL) * (D * D), true);
+        }
     }
 }
 
@@ -304,9 +447,7 @@ __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cp
             y[l].x += 1.0;
         }
         if (live) {
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                if (PT::has(i, l)) dst[PT::idx(i, l)] = dab[i];
+            store_col<D, stored_from_tri(D, UMASK), l>(dst, dab);
         }
       }
         so_columns<D, UMASK, l + 1>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
@@ -393,79 +534,6 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
 // For structural patterns with few non-zeros the whole forward state / co-state fits in one thread's registers,
 // so the chunk aggregate and the backward gradient sweep need no shared memory, no cp.async staging and no
 // cross-lane reduction: one thread = one (pulse, chunk); step matrices stream from HBM in the compact layout.
-template <int D, u64 CM>
-struct PMat {                       // matrix restricted to the pattern, stored compactly
-    cplx v[Pat<D, CM>::nnz];
-    __device__ __forceinline__ void zero() {
-#pragma unroll
-        for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = cmk(0.0, 0.0);
-    }
-    __device__ __forceinline__ void identity() {
-#pragma unroll
-        for (int j = 0; j < D; ++j)
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-                if (Pat<D, CM>::has(i, j)) v[Pat<D, CM>::idx(i, j)] = cmk(i == j ? 1.0 : 0.0, 0.0);
-    }
-    __device__ __forceinline__ void load(const cplx* __restrict__ p) {
-#pragma unroll
-        for (int i = 0; i < Pat<D, CM>::nnz; ++i) v[i] = p[i];
-    }
-};
-// dense d x d (column-major) <-> pattern
-template <int D, u64 CM>
-__device__ __forceinline__ void pmat_from_dense(PMat<D, CM>& m, const cplx* __restrict__ p) {
-#pragma unroll
-    for (int j = 0; j < D; ++j)
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-            if (Pat<D, CM>::has(i, j)) m.v[Pat<D, CM>::idx(i, j)] = p[i + D * j];
-}
-// unit_inert: entries (l,l) of inert levels (diagonal bit absent) are written as 1 (products of propagators), else 0
-template <int D, u64 CM>
-__device__ __forceinline__ void pmat_to_dense(const PMat<D, CM>& m, cplx* __restrict__ p, bool unit_inert) {
-#pragma unroll
-    for (int j = 0; j < D; ++j)
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-            p[i + D * j] = Pat<D, CM>::has(i, j) ? m.v[Pat<D, CM>::idx(i, j)] : cmk((i == j && unit_inert) ? 1.0 : 0.0, 0.0);
-}
-// C = op(A) B with op = none (ADJ = false) or conjugate transpose (ADJ = true); the closure pattern is closed under
-// products and adjoints, so the result stays inside it.
-template <int D, u64 CM, bool ADJ, bool ACC>
-__device__ __forceinline__ void pmat_mul(PMat<D, CM>& c, const PMat<D, CM>& a, const PMat<D, CM>& b) {
-    typedef Pat<D, CM> PT;
-#pragma unroll
-    for (int j = 0; j < D; ++j)
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            if (!PT::has(i, j)) continue;
-            cplx acc = ACC ? c.v[PT::idx(i, j)] : cmk(0.0, 0.0);
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                if (!PT::has(k, j)) continue;
-                if (ADJ) { if (PT::has(k, i)) cfma_conj(acc, a.v[PT::idx(k, i)], b.v[PT::idx(k, j)]); }
-                else { if (PT::has(i, k)) cfma(acc, a.v[PT::idx(i, k)], b.v[PT::idx(k, j)]); }
-            }
-            c.v[PT::idx(i, j)] = acc;
-        }
-}
-// Re tr(A B)
-template <int D, u64 CM>
-__device__ __forceinline__ double pmat_retrace(const PMat<D, CM>& a, const PMat<D, CM>& b) {
-    typedef Pat<D, CM> PT;
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j)
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-            if (PT::has(i, j) && PT::has(j, i)) {
-                const cplx x = a.v[PT::idx(i, j)], y = b.v[PT::idx(j, i)];
-                s = fma(x.x, y.x, s); s = fma(-x.y, y.y, s);
-            }
-    return s;
-}
-
 // Chunk aggregates, one thread per (pulse, chunk): Q <- U_k Q ; Wl_e <- U_k Wl_e + D_k^e Q_old
 template <int D, u64 CM>
 __global__ void __launch_bounds__(128)
