@@ -276,8 +276,12 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         for (int v = 0; v < RG_MAX_VARS; ++v) tp.maskVar[v] = 0;
         for (int e = 0; e < RG_MAX_ERR; ++e) tp.maskErr[e] = 0;
         for (auto& en : he) {
-            colw[(size_t)en.term * d + en.col] += std::sqrt(en.vr * en.vr + en.vi * en.vi);
             if (en.row > en.col) continue;
+            // column weights from the upper triangle, mirrored: the assembled matrix is (skew-)Hermitian, so entry (i,k)
+            // also stands for (k,i); terms that only hold lower-triangle entries are the mirror images and carry no weight
+            const double aw = std::sqrt(en.vr * en.vr + en.vi * en.vi);
+            colw[(size_t)en.term * d + en.col] += aw;
+            if (en.row != en.col) colw[(size_t)en.term * d + en.row] += aw;
             const int pos = en.col * (en.col + 1) / 2 + en.row;
             lists[pos].push_back({en.term, {en.vr, en.vi}});
             used[en.term] = 1;

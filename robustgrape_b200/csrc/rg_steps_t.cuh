@@ -26,11 +26,15 @@ struct TriPlanDev {
     unsigned maskErr[RG_MAX_ERR];    // ... by terms of error source e
 };
 
-struct StagedPlan { const int* ptr; const int* term; const cplx* val; const double* colw; const int* used; const DevTerm* terms; };
+struct StagedPlan {
+    const int* ptr; const int* term; const cplx* val; const double* colw; const int* used; const DevTerm* terms;
+    const cplx* dense;        // [nterms][npos] matrix value of term t at upper-triangle position pos (0 where absent)
+};
 __host__ __device__ inline size_t staged_plan_bytes(int nterms, int nent, int d) {
     const int npos = d * (d + 1) / 2;
     return rg_align16((size_t)nterms * sizeof(DevTerm)) + rg_align16((size_t)(npos + 1) * 4) + rg_align16((size_t)nent * 4) +
-           rg_align16((size_t)nent * 16) + rg_align16((size_t)nterms * d * 8) + rg_align16((size_t)nterms * 4);
+           rg_align16((size_t)nent * 16) + rg_align16((size_t)nterms * d * 8) + rg_align16((size_t)nterms * 4) +
+           rg_align16((size_t)nterms * npos * 16);
 }
 __device__ inline StagedPlan stage_plan(const DevProblem& P, const TriPlanDev& tp, unsigned char* sm) {
     const int npos = P.d * (P.d + 1) / 2;
@@ -40,7 +44,9 @@ __device__ inline StagedPlan stage_plan(const DevProblem& P, const TriPlanDev& t
     int* term = reinterpret_cast<int*>(p); p += rg_align16((size_t)tp.nent * 4);
     double* val = reinterpret_cast<double*>(p); p += rg_align16((size_t)tp.nent * 16);
     double* colw = reinterpret_cast<double*>(p); p += rg_align16((size_t)P.nterms * P.d * 8);
-    int* used = reinterpret_cast<int*>(p);
+    int* used = reinterpret_cast<int*>(p); p += rg_align16((size_t)P.nterms * 4);
+    double* dense = reinterpret_cast<double*>(p);
+    for (int i = threadIdx.x; i < 2 * P.nterms * npos; i += blockDim.x) dense[i] = 0.0;
     const int nt4 = P.nterms * (int)(sizeof(DevTerm) / 4);
     for (int i = threadIdx.x; i < nt4; i += blockDim.x) t32[i] = reinterpret_cast<const int*>(P.terms)[i];
     for (int i = threadIdx.x; i <= npos; i += blockDim.x) ptr[i] = tp.ptr[i];
@@ -48,8 +54,52 @@ __device__ inline StagedPlan stage_plan(const DevProblem& P, const TriPlanDev& t
     for (int i = threadIdx.x; i < P.nterms * P.d; i += blockDim.x) colw[i] = tp.colw[i];
     for (int i = threadIdx.x; i < P.nterms; i += blockDim.x) used[i] = tp.used[i];
     __syncthreads();
-    StagedPlan s{ptr, term, reinterpret_cast<const cplx*>(val), colw, used, reinterpret_cast<const DevTerm*>(t32)};
+    for (int pos = threadIdx.x; pos < npos; pos += blockDim.x)          // one thread per position: no write conflicts
+        for (int e = ptr[pos]; e < ptr[pos + 1]; ++e) {
+            dense[2 * (term[e] * npos + pos)] += val[2 * e];
+            dense[2 * (term[e] * npos + pos) + 1] += val[2 * e + 1];
+        }
+    __syncthreads();
+    StagedPlan s{ptr, term, reinterpret_cast<const cplx*>(val), colw, used, reinterpret_cast<const DevTerm*>(t32),
+                 reinterpret_cast<const cplx*>(dense)};
     return s;
+}
+
+template <int D, unsigned UMASK, int l, bool CHECK>
+__device__ __forceinline__ void horner_loop_tri(const cplx (&ta)[Tri<D>::n], const cplx (&td)[Tri<D>::n], unsigned mA, unsigned mD,
+                                                int m, cplx (&y)[D], cplx (&dl)[D]) {
+    typedef Pat<D, closure_from_tri(D, UMASK)> PT;
+    for (int j = m - 1; j >= 1; --j) {
+        const double inv = c_inv_j[j];
+        cplx t[D], u[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) { t[i] = cmk(0.0, 0.0); u[i] = cmk(0.0, 0.0); }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+#pragma unroll
+            for (int i = 0; i <= k; ++i) {
+                const int pos = Tri<D>::idx(i, k);
+                if (!((UMASK >> pos) & 1u)) continue;
+                if (!PT::has(k, l) && !PT::has(i, l)) continue;      // both operands structurally zero in this column
+                if (!CHECK || ((mA >> pos) & 1u)) {
+                    const cplx a = ta[pos];
+                    if (PT::has(k, l)) { cfma(t[i], a, y[k]); cfma(u[i], a, dl[k]); }
+                    if (i != k && PT::has(i, l)) { cfma_nconj(t[k], a, y[i]); cfma_nconj(u[k], a, dl[i]); }
+                }
+                if (!CHECK || ((mD >> pos) & 1u)) {
+                    const cplx d = td[pos];
+                    if (PT::has(k, l)) cfma(u[i], d, cadd(y[k], dl[k]));
+                    if (i != k && PT::has(i, l)) cfma_nconj(u[k], d, cadd(y[i], dl[i]));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            y[i] = cscale(t[i], inv);
+            if (i == l) y[i].x += 1.0;
+            dl[i] = cscale(u[i], inv);
+        }
+    }
 }
 
 // (value, difference) Horner recurrence for one column l with register-resident triangles.
@@ -78,37 +128,10 @@ __device__ __forceinline__ void horner_col_tri(const cplx (&ta)[Tri<D>::n], cons
 #pragma unroll
         for (int i = 0; i < D; ++i) if (i == l) y[i].x += 1.0;
     }
-    for (int j = m - 1; j >= 1; --j) {
-        const double inv = c_inv_j[j];
-        cplx t[D], u[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) { t[i] = cmk(0.0, 0.0); u[i] = cmk(0.0, 0.0); }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-#pragma unroll
-            for (int i = 0; i <= k; ++i) {
-                const int pos = Tri<D>::idx(i, k);
-                if (!((UMASK >> pos) & 1u)) continue;
-                if (!PT::has(k, l) && !PT::has(i, l)) continue;      // both operands structurally zero in this column
-                if (!MASKED || ((mA >> pos) & 1u)) {
-                    const cplx a = ta[pos];
-                    if (PT::has(k, l)) { cfma(t[i], a, y[k]); cfma(u[i], a, dl[k]); }
-                    if (i != k && PT::has(i, l)) { cfma_nconj(t[k], a, y[i]); cfma_nconj(u[k], a, dl[i]); }
-                }
-                if (!MASKED || ((mD >> pos) & 1u)) {
-                    const cplx d = td[pos];
-                    if (PT::has(k, l)) cfma(u[i], d, cadd(y[k], dl[k]));
-                    if (i != k && PT::has(i, l)) cfma_nconj(u[k], d, cadd(y[i], dl[i]));
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            y[i] = cscale(t[i], inv);
-            if (i == l) y[i].x += 1.0;
-            dl[i] = cscale(u[i], inv);
-        }
-    }
+    // run-time masks cost an ISETP per position and iteration; when both matrices fill the compile-time pattern (the usual
+    // case for the pre-instantiated Rydberg patterns) take the test-free loop
+    if (!MASKED || ((mA & mD & UMASK) == UMASK)) horner_loop_tri<D, UMASK, l, false>(ta, td, mA, mD, m, y, dl);
+    else horner_loop_tri<D, UMASK, l, true>(ta, td, mA, mD, m, y, dl);
 }
 
 // Column l of a compact (pattern) matrix to global memory. With an even number of stored elements every matrix starts on
@@ -255,29 +278,30 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     constexpr int NP = Tri<D>::n;
     typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
-    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     const int Np = aggL ? nc * aggL : P.N;                       // padded steps per pulse
     const long long total = (long long)B * Np;
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_grid = item < total;
     if (!in_grid) item = total - 1;
-    const int b = (int)(item / Np), kp = (int)(item % Np);
+    int b, kp;
+    if (total < (1ll << 31)) { b = (int)((unsigned)item / (unsigned)Np); kp = (int)((unsigned)item - (unsigned)b * (unsigned)Np); }
+    else { b = (int)(item / Np); kp = (int)(item % Np); }
     const bool live = in_grid && kp < P.N;
     const int k = min(kp, P.N - 1);
-    cplx* smU = aggL ? reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(smem) + agg_off) + threadIdx.x : nullptr;
+    // the control values are requested before the plan is staged so that their latency hides behind it
     const double* xp = X + (size_t)b * P.nx;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    cplx* smU = aggL ? reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(smem) + agg_off) + threadIdx.x : nullptr;
     cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)PT::nnz;            // object 0 of this step
     const size_t objS = (size_t)P.wsB * P.N * PT::nnz;                    // stride between objects
     const int nt = P.nterms, nv = P.nvar, ne = P.e, nfo = nv + ne;
 
-    cplx ca[RG_T_MAX_TERMS], cd[RG_T_MAX_TERMS];     // (-i dt) * coefficient, value and difference
     cplx ta[NP], td[NP];
     int m = 0;
     for (int o = 0; o < max(nfo, 1); ++o) {
-        // ---- coefficients of this pass (and of A on the first pass)
         int sp_ = RG_S_NONE, ix = 0, es = -3;
         double h = 0.0, errv = 0.0;
         if (nfo > 0 && o < nv) {
@@ -286,41 +310,45 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             h = __dsub_rn(__dadd_rn(v, P.eps), v);                 // the step actually taken (:50)
         } else if (nfo > 0) { es = o - nv; errv = P.eps; }
         EvalCtx ec{xk, xadd, errv, P.table, P.N, k};
+        // ---- triangles of A = -i dt H (first pass) and of this pass's dA, one term at a time: the coefficient is consumed
+        // as soon as it is known (no per-thread coefficient arrays), and the column-sum bound of ||A||_1 rides along
+        double colsum[D];
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) colsum[kk] = 0.0;
+#pragma unroll
+        for (int pos = 0; pos < NP; ++pos) { if (o == 0) ta[pos] = cmk(0, 0); td[pos] = cmk(0, 0); }
         for (int t = 0; t < nt; ++t) {
-            cplx base = cmk(0, 0), del = cmk(0, 0);
             const DevTerm& tm = sp.terms[t];
             const bool isH0 = tm.owner == RG_OWNER_H0;
-            if (sp.used[t] && (isH0 || tm.owner == es)) term_coef(tm, ec, sp_, ix, h, base, del);
-            if (o == 0) ca[t] = isH0 ? cmk(base.y * P.dt, -base.x * P.dt) : cmk(0, 0);
+            // H0 terms: value on the first pass, difference on variable passes; error terms: only on their own pass
+            if (!sp.used[t] || !((isH0 && (o == 0 || es < 0)) || tm.owner == es)) continue;
+            cplx base, del;
+            term_coef(tm, ec, sp_, ix, h, base, del);
+            const cplx ca = isH0 ? cmk(base.y * P.dt, -base.x * P.dt) : cmk(0, 0);     // (-i dt) * coefficient
             const cplx dsel = isH0 ? del : base;                   // error terms enter with their value at err = eps
-            cd[t] = (isH0 && es >= 0) ? cmk(0, 0) : cmk(dsel.y * P.dt, -dsel.x * P.dt);
-        }
-        // ---- triangles
+            const cplx cd = (isH0 && es >= 0) ? cmk(0, 0) : cmk(dsel.y * P.dt, -dsel.x * P.dt);
+            const cplx* dv = sp.dense + t * NP;
 #pragma unroll
-        for (int pos = 0; pos < NP; ++pos) {
-            if (!((UMASK >> pos) & 1u)) continue;
-            cplx a = cmk(0, 0), d = cmk(0, 0);
-            for (int e = sp.ptr[pos]; e < sp.ptr[pos + 1]; ++e) {
-                const int t = sp.term[e];
-                const cplx v = sp.val[e];
-                if (o == 0) cfma(a, ca[t], v);
-                cfma(d, cd[t], v);
+            for (int pos = 0; pos < NP; ++pos) {
+                if (!((UMASK >> pos) & 1u)) continue;
+                const cplx v = dv[pos];
+                if (v.x == 0.0 && v.y == 0.0) continue;            // warp-uniform
+                if (o == 0) cfma(ta[pos], ca, v);
+                cfma(td[pos], cd, v);
             }
-            if (o == 0) ta[pos] = a;
-            td[pos] = d;
+            if (o == 0 && isH0) {
+                // |c| <= max(|re|,|im|) + (sqrt2 - 1) min(|re|,|im|)  (strict upper bound, <= 8.3 % high; no square roots)
+                const double ax = fabs(ca.x), ay = fabs(ca.y);
+                const double w = fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) colsum[kk] = fma(w, sp.colw[t * D + kk], colsum[kk]);
+            }
         }
         if (o == 0) {
-            // ||A||_1 <= max_k sum_t |c_t| * ||M_t[:,k]||_1
-            // |c| <= max(|re|,|im|) + (sqrt2 - 1) min(|re|,|im|)  (strict upper bound, <= 8.3 % high; no square roots)
+            // ||A||_1 <= max_k sum_t |c_t| * (column-k weight of M_t, upper triangle mirrored: A is skew-Hermitian)
             double nrm = 0.0;
-            for (int kk = 0; kk < D; ++kk) {
-                double s = 0.0;
-                for (int t = 0; t < nt; ++t) {
-                    const double ax = fabs(ca[t].x), ay = fabs(ca[t].y);
-                    s += (fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay)) * sp.colw[t * D + kk];
-                }
-                nrm = fmax(nrm, s);
-            }
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk) nrm = fmax(nrm, colsum[kk]);
             m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
             m = __reduce_max_sync(0xffffffffu, m);
             if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 2); m = 18; }
