@@ -13,6 +13,15 @@
 #include "rg_smalld.cuh"
 
 #define RG_T_MAX_TERMS 16
+#ifndef RG_STEPS_T_CTAS
+#define RG_STEPS_T_CTAS 6      // resident CTAs per SM requested for the sparse-pattern k_steps_t (register cap 65536 / (128 n))
+#endif
+#ifndef RG_AGG_T_CTAS
+#define RG_AGG_T_CTAS 1
+#endif
+#ifndef RG_GRAD_T_CTAS
+#define RG_GRAD_T_CTAS 1
+#endif
 
 struct TriPlanDev {
     int nent;                 // plan entries
@@ -269,7 +278,7 @@ __device__ __forceinline__ double pmat_retrace(const PMat<D, CM>& a, const PMat<
 }
 
 template <int D, unsigned UMASK>
-__global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : 4)
+__global__ void __launch_bounds__(128, (UMASK == ((1u << (D * (D + 1) / 2)) - 1u)) ? 2 : RG_STEPS_T_CTAS)
 k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
           int* __restrict__ status, int aggL = 0, int nc = 0, cplx* __restrict__ Qb = nullptr, int agg_off = 0) {
     // aggL > 0 (a power of two <= 32, no error sources): the time axis is padded to nc*aggL so that every aligned group of
@@ -564,7 +573,7 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
 // cross-lane reduction: one thread = one (pulse, chunk); step matrices stream from HBM in the compact layout.
 // Chunk aggregates, one thread per (pulse, chunk): Q <- U_k Q ; Wl_e <- U_k Wl_e + D_k^e Q_old
 template <int D, u64 CM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RG_AGG_T_CTAS)
 k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, cplx* __restrict__ Qb, cplx* __restrict__ Wlb) {
     typedef Pat<D, CM> PT;
     typedef PMat<D, CM> M;
@@ -607,7 +616,7 @@ k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__
 // Backward gradient sweep, one thread per (pulse, chunk), fidelity role only (ERR roles use k_grad):
 //   out0[b*nx + p*k + v] = scale0 * Re tr(G_k dU_k^v C_{k-1})
 template <int D, u64 CM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RG_GRAD_T_CTAS)
 k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, const cplx* __restrict__ Cb,
          const cplx* __restrict__ Gb, double* __restrict__ out0, double scale0, double* __restrict__ addS) {
     typedef Pat<D, CM> PT;
