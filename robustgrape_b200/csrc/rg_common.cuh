@@ -57,6 +57,18 @@ __device__ __forceinline__ cplx cconj(cplx a) { return cmk(a.x, -a.y); }
 __device__ __forceinline__ void ld256(const cplx* __restrict__ p, cplx& a, cplx& b) {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
 }
+// Software prefetch of one 128-byte line (a compact step matrix) for the thread-per-chunk sweeps: costs no registers,
+// unlike loading the next step's operands early. RG_PREFETCH_LEVEL: 0 off, 1 into L1, 2 into L2.
+#ifndef RG_PREFETCH_LEVEL
+#define RG_PREFETCH_LEVEL 1
+#endif
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if RG_PREFETCH_LEVEL == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif RG_PREFETCH_LEVEL == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 __device__ __forceinline__ void st256(cplx* __restrict__ p, const cplx a, const cplx b) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 }

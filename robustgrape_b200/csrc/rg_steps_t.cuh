@@ -16,11 +16,11 @@
 #ifndef RG_STEPS_T_CTAS
 #define RG_STEPS_T_CTAS 6      // resident CTAs per SM requested for the sparse-pattern k_steps_t (register cap 65536 / (128 n))
 #endif
-#ifndef RG_AGG_T_CTAS
-#define RG_AGG_T_CTAS 1
+#ifndef RG_SO_T_CTAS
+#define RG_SO_T_CTAS 4
 #endif
-#ifndef RG_GRAD_T_CTAS
-#define RG_GRAD_T_CTAS 1
+#ifndef RG_AGG_T_CTAS
+#define RG_AGG_T_CTAS 3        // 168 registers, no spills; the gradient sweeps spill (and slow down) under any cap
 #endif
 
 struct TriPlanDev {
@@ -213,6 +213,10 @@ struct PMat {                       // matrix restricted to the pattern, stored 
             for (int i = 0; i < D; ++i)
                 if (Pat<D, CM>::has(i, j)) v[Pat<D, CM>::idx(i, j)] = cmk(i == j ? 1.0 : 0.0, 0.0);
     }
+    static __device__ __forceinline__ void prefetch(const cplx* __restrict__ p) {
+#pragma unroll
+        for (int i = 0; i < Pat<D, CM>::nnz; i += 8) prefetch_line(p + i);           // 8 complex numbers per 128-byte line
+    }
     __device__ __forceinline__ void load(const cplx* __restrict__ p) {
         if constexpr ((Pat<D, CM>::nnz & 1) == 0) {        // matrices start on 32-byte boundaries: 256-bit loads
 #pragma unroll
@@ -396,10 +400,10 @@ k_steps_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
 // ------------------------------------------------------------------ mixed second differences, thread per step
 // t += M v for a skew-Hermitian M given by its upper triangle; column l of the closure pattern decides which
 // components of v can be non-zero.  mrt: run-time (warp-uniform) mask of M within the compile-time UMASK.
-template <int D, unsigned UMASK, int l>
+template <int D, unsigned UMASK, int l, bool CHECK = true>
 __device__ __forceinline__ void tri_matvec_acc(cplx (&t)[D], const cplx (&tri)[Tri<D>::n], unsigned mrt, const cplx (&v)[D]) {
     typedef Pat<D, closure_from_tri(D, UMASK)> PT;
-    constexpr bool MASKED = (UMASK != ((1u << Tri<D>::n) - 1u));
+    constexpr bool MASKED = CHECK && (UMASK != ((1u << Tri<D>::n) - 1u));
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
@@ -429,7 +433,7 @@ __device__ __forceinline__ void tri_column(cplx (&y)[D], const cplx (&tri)[Tri<D
         }
 }
 
-template <int D, unsigned UMASK, int l>
+template <int D, unsigned UMASK, int l, bool CHECK>
 __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cplx (&tal)[Tri<D>::n], const cplx (&tbe)[Tri<D>::n],
                                            const cplx (&tga)[Tri<D>::n], unsigned mA, unsigned mAl, unsigned mBe, int m,
                                            bool live, cplx* __restrict__ dst) {
@@ -449,36 +453,36 @@ __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cp
             // dab' = (A dab + al (db + dab) + be (da + dab) + ga (y + da + db + dab)) / j
 #pragma unroll
             for (int i = 0; i < D; ++i) acc[i] = cmk(0.0, 0.0);
-            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, dab);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, ta, mA, dab);
 #pragma unroll
             for (int i = 0; i < D; ++i) s[i] = cadd(db[i], dab[i]);
-            tri_matvec_acc<D, UMASK, l>(acc, tal, mAl, s);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, tal, mAl, s);
 #pragma unroll
             for (int i = 0; i < D; ++i) s[i] = cadd(da[i], dab[i]);
-            tri_matvec_acc<D, UMASK, l>(acc, tbe, mBe, s);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, tbe, mBe, s);
 #pragma unroll
             for (int i = 0; i < D; ++i) s[i] = cadd(cadd(y[i], da[i]), cadd(db[i], dab[i]));
-            tri_matvec_acc<D, UMASK, l>(acc, tga, mBe, s);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, tga, mBe, s);
 #pragma unroll
             for (int i = 0; i < D; ++i) dab[i] = cscale(acc[i], inv);
             // da' = (A da + al (y + da)) / j
 #pragma unroll
             for (int i = 0; i < D; ++i) { acc[i] = cmk(0.0, 0.0); s[i] = cadd(y[i], da[i]); }
-            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, da);
-            tri_matvec_acc<D, UMASK, l>(acc, tal, mAl, s);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, ta, mA, da);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, tal, mAl, s);
 #pragma unroll
             for (int i = 0; i < D; ++i) da[i] = cscale(acc[i], inv);
             // db' = (A db + be (y + db)) / j
 #pragma unroll
             for (int i = 0; i < D; ++i) { acc[i] = cmk(0.0, 0.0); s[i] = cadd(y[i], db[i]); }
-            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, db);
-            tri_matvec_acc<D, UMASK, l>(acc, tbe, mBe, s);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, ta, mA, db);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, tbe, mBe, s);
 #pragma unroll
             for (int i = 0; i < D; ++i) db[i] = cscale(acc[i], inv);
             // y' = I + A y / j
 #pragma unroll
             for (int i = 0; i < D; ++i) acc[i] = cmk(0.0, 0.0);
-            tri_matvec_acc<D, UMASK, l>(acc, ta, mA, y);
+            tri_matvec_acc<D, UMASK, l, CHECK>(acc, ta, mA, y);
 #pragma unroll
             for (int i = 0; i < D; ++i) y[i] = cscale(acc[i], inv);
             y[l].x += 1.0;
@@ -487,34 +491,35 @@ __device__ __forceinline__ void so_columns(const cplx (&ta)[Tri<D>::n], const cp
             store_col<D, stored_from_tri(D, UMASK), l>(dst, dab);
         }
       }
-        so_columns<D, UMASK, l + 1>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
+        so_columns<D, UMASK, l + 1, CHECK>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
     }
 }
 
 // One thread per time step: mixed second differences d2U^{v,e} at (eps2, eps2) for every (variable, error source).
 // Only instantiated for structural masks small enough to keep four triangles in registers.
 template <int D, unsigned UMASK>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, RG_SO_T_CTAS)
 k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, cplx* __restrict__ ws,
              int* __restrict__ status) {
     constexpr int NP = Tri<D>::n;
     typedef Pat<D, stored_from_tri(D, UMASK)> PT;
     extern __shared__ cplx smem[];
-    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     const long long total = (long long)B * P.N;
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = item < total;
     if (!live) item = total - 1;
-    const int b = (int)(item / P.N), k = (int)(item % P.N);
+    int b, k;
+    if (total < (1ll << 31)) { b = (int)((unsigned)item / (unsigned)P.N); k = (int)((unsigned)item - (unsigned)b * (unsigned)P.N); }
+    else { b = (int)(item / P.N); k = (int)(item % P.N); }
     const double* xp = X + (size_t)b * P.nx;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
     cplx* wsk = ws + ((size_t)b * P.N + k) * (size_t)PT::nnz;
     const size_t objS = (size_t)P.wsB * P.N * PT::nnz;
     const int nt = P.nterms, nv = P.nvar, ne = P.e;
 
-    cplx cA[RG_T_MAX_TERMS], cB[RG_T_MAX_TERMS], cC[RG_T_MAX_TERMS];
     cplx ta[NP], tal[NP], tbe[NP], tga[NP];
     int m = 0;
     for (int e = 0; e < ne; ++e)
@@ -523,46 +528,48 @@ k_steps_so_t(const DevProblem P, const TriPlanDev tp, const double* __restrict__
             const double val = (sp_ == RG_S_MAIN) ? xk[ix] : xadd[ix];
             const double h2 = __dsub_rn(__dadd_rn(val, P.eps2), val);
             EvalCtx ec{xk, xadd, P.eps2, P.table, P.N, k};
+            // triangles, one term at a time (see k_steps_t):  A : H0 value | alpha : H0 difference in v |
+            // beta : error value at eps2 | gamma : error difference in v at eps2
+            double colsum[D];
+#pragma unroll
+            for (int kk = 0; kk < D; ++kk) colsum[kk] = 0.0;
+#pragma unroll
+            for (int pos = 0; pos < NP; ++pos) { ta[pos] = cmk(0, 0); tal[pos] = cmk(0, 0); tbe[pos] = cmk(0, 0); tga[pos] = cmk(0, 0); }
             for (int t = 0; t < nt; ++t) {
-                cplx base = cmk(0, 0), del = cmk(0, 0);
                 const DevTerm& tm = sp.terms[t];
                 const bool isH0 = tm.owner == RG_OWNER_H0;
-                if (sp.used[t] && (isH0 || tm.owner == e)) term_coef(tm, ec, sp_, ix, h2, base, del);
+                if (!sp.used[t] || !(isH0 || tm.owner == e)) continue;
+                cplx base, del;
+                term_coef(tm, ec, sp_, ix, h2, base, del);
                 const cplx sb = cmk(base.y * P.dt, -base.x * P.dt), sd2 = cmk(del.y * P.dt, -del.x * P.dt);
-                cA[t] = isH0 ? sb : cmk(0, 0);        // A      : H0 value
-                cB[t] = isH0 ? sd2 : sb;              // alpha  : H0 difference in v   | beta : error value at eps2
-                cC[t] = isH0 ? cmk(0, 0) : sd2;       // gamma  : error difference in v at eps2
-            }
+                const cplx* dv = sp.dense + t * NP;
 #pragma unroll
-            for (int pos = 0; pos < NP; ++pos) {
-                if (!((UMASK >> pos) & 1u)) continue;
-                cplx a = cmk(0, 0), al = cmk(0, 0), be = cmk(0, 0), ga = cmk(0, 0);
-                for (int q = sp.ptr[pos]; q < sp.ptr[pos + 1]; ++q) {
-                    const int t = sp.term[q];
-                    const cplx vv = sp.val[q];
-                    const bool isH0 = sp.terms[t].owner == RG_OWNER_H0;
-                    cfma(a, cA[t], vv);
-                    if (isH0) cfma(al, cB[t], vv); else cfma(be, cB[t], vv);
-                    cfma(ga, cC[t], vv);
+                for (int pos = 0; pos < NP; ++pos) {
+                    if (!((UMASK >> pos) & 1u)) continue;
+                    const cplx vv = dv[pos];
+                    if (vv.x == 0.0 && vv.y == 0.0) continue;          // warp-uniform
+                    if (isH0) { cfma(ta[pos], sb, vv); cfma(tal[pos], sd2, vv); }
+                    else { cfma(tbe[pos], sb, vv); cfma(tga[pos], sd2, vv); }
                 }
-                ta[pos] = a; tal[pos] = al; tbe[pos] = be; tga[pos] = ga;
+                if (e == 0 && v == 0 && isH0) {
+                    const double ax = fabs(sb.x), ay = fabs(sb.y);
+                    const double w = fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay);
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) colsum[kk] = fma(w, sp.colw[t * D + kk], colsum[kk]);
+                }
             }
             if (e == 0 && v == 0) {
                 double nrm = 0.0;
-                for (int kk = 0; kk < D; ++kk) {
-                    double s = 0.0;
-                    for (int t = 0; t < nt; ++t) {
-                        const double ax = fabs(cA[t].x), ay = fabs(cA[t].y);
-                        s += (fmax(ax, ay) + 0.41421356237309515 * fmin(ax, ay)) * sp.colw[t * D + kk];
-                    }
-                    nrm = fmax(nrm, s);
-                }
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) nrm = fmax(nrm, colsum[kk]);
                 m = taylor_degree(nrm * 1.001 + 2.0 * P.eps2 * P.dt);
                 m = __reduce_max_sync(0xffffffffu, m);
                 if (m == 99) { if ((threadIdx.x & 31) == 0) atomicOr(status, 2); m = 18; }
             }
-            so_columns<D, UMASK, 0>(ta, tal, tbe, tga, tp.maskA, tp.maskVar[v], tp.maskErr[e], m, live,
-                                    wsk + (size_t)(1 + nv + ne + e * nv + v) * objS);
+            cplx* dst = wsk + (size_t)(1 + nv + ne + e * nv + v) * objS;
+            const unsigned mA = tp.maskA, mAl = tp.maskVar[v], mBe = tp.maskErr[e];
+            if ((mA & mAl & mBe & UMASK) == UMASK) so_columns<D, UMASK, 0, false>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
+            else so_columns<D, UMASK, 0, true>(ta, tal, tbe, tga, mA, mAl, mBe, m, live, dst);
         }
 }
 
@@ -616,7 +623,7 @@ k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__
 // Backward gradient sweep, one thread per (pulse, chunk), fidelity role only (ERR roles use k_grad):
 //   out0[b*nx + p*k + v] = scale0 * Re tr(G_k dU_k^v C_{k-1})
 template <int D, u64 CM>
-__global__ void __launch_bounds__(128, RG_GRAD_T_CTAS)
+__global__ void __launch_bounds__(128)
 k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, const cplx* __restrict__ Cb,
          const cplx* __restrict__ Gb, double* __restrict__ out0, double scale0, double* __restrict__ addS) {
     typedef Pat<D, CM> PT;
@@ -644,7 +651,7 @@ k_grad_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ ws, 
     for (int k = k1 - 1; k >= k0; --k) {
         const cplx* wsk = wsb + (size_t)k * PT::nnz;
         M un;
-        if (k > k0) un.load(wsb + (size_t)(k - 1) * PT::nnz);       // prefetch the next step's U
+        if (k > k0) un.load(wsb + (size_t)(k - 1) * PT::nnz);       // prefetch the next step's U (a cache prefetch of dU measured slower)
         M cp; pmat_mul<D, CM, true, false>(cp, u, c);                         // C_{k-1} = U_k^dag C_k
         for (int v = 0; v < nv; ++v) {
             M du; du.load(wsk + (size_t)(1 + v) * objS);
@@ -696,6 +703,11 @@ k_grad_err_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__ 
     }
     for (int k = k1 - 1; k >= k0; --k) {
         const cplx* wsk = wsb + (size_t)k * PT::nnz;
+        if (k > k0) {                          // next step's operands on their way while this step is computed
+            const cplx* nx = wsk - PT::nnz;
+            M::prefetch(nx); M::prefetch(nx + (size_t)(1 + nv + es) * objS);
+            for (int v = 0; v < nv; ++v) { M::prefetch(nx + (size_t)(1 + v) * objS); M::prefetch(nx + (size_t)(1 + nv + ne + es * nv + v) * objS); }
+        }
         {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
             M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + es) * objS);
             M cp; pmat_mul<D, CM, true, false>(cp, u, c);
