@@ -158,22 +158,30 @@ __host__ __device__ constexpr int pat_prev_row(int i, int l) {          // previ
         if (Pat<D, CMS>::has(r, l)) return r;
     return -1;
 }
+// (row index as a template parameter: every pattern query below is a constant expression, nothing is evaluated at run time)
+template <int D, u64 CMS, int l, int i>
+__device__ __forceinline__ void store_col_row(cplx* __restrict__ dst, const cplx (&v)[D]) {
+    typedef Pat<D, CMS> PT;
+    if constexpr (i < D) {
+        if constexpr (PT::has(i, l)) {
+            constexpr bool PAIRS = (PT::nnz & 1) == 0;
+            constexpr int prev = pat_prev_row<D, CMS>(i, l), next = pat_next_row<D, CMS>(i, l);
+            constexpr int me = PT::idx(i, l);
+            // pairs are formed greedily from the top of the column: element i is the second of a pair iff the element before
+            // it has an even compact index (the compact indices of a column are consecutive)
+            constexpr bool second = PAIRS && prev >= 0 && ((me - 1) & 1) == 0;
+            constexpr bool first = PAIRS && next < D && (me & 1) == 0;
+            if constexpr (!second) {
+                if constexpr (first) st256(dst + me, v[i], v[next < D ? next : i]);
+                else dst[me] = v[i];
+            }
+        }
+        store_col_row<D, CMS, l, i + 1>(dst, v);
+    }
+}
 template <int D, u64 CMS, int l>
 __device__ __forceinline__ void store_col(cplx* __restrict__ dst, const cplx (&v)[D]) {
-    typedef Pat<D, CMS> PT;
-    constexpr bool PAIRS = (PT::nnz & 1) == 0;
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        if (!PT::has(i, l)) continue;
-        const int prev = pat_prev_row<D, CMS>(i, l), next = pat_next_row<D, CMS>(i, l);
-        // pairs are formed greedily from the top of the column: element i is the second of a pair iff the element before
-        // it has an even compact index (the compact indices of a column are consecutive)
-        const bool second = PAIRS && prev >= 0 && (PT::idx(prev, l) & 1) == 0;
-        if (second) continue;
-        const bool first = PAIRS && next < D && (PT::idx(i, l) & 1) == 0;
-        if (first) st256(dst + PT::idx(i, l), v[i], v[next < D ? next : i]);
-        else dst[PT::idx(i, l)] = v[i];
-    }
+    store_col_row<D, CMS, l, 0>(dst, v);
 }
 
 template <int D, unsigned UMASK, int l>
