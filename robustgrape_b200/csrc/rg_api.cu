@@ -42,6 +42,7 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     *c->h_status = 0;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char* s = getenv("RG_HOST_SLABS")) c->host_slabs = std::max(1, atoi(s));
+    if (const char* s = getenv("RG_HOST_SLAB_MIN")) c->host_slab_min = std::max(1, atoi(s));
     cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (const char* s = getenv("RG_WS_LIMIT_GB")) c->ws_limit = (size_t)atof(s) * ((size_t)1 << 30);
@@ -389,7 +390,7 @@ extern "C" int rg_cost_and_grad_batch_dev(rg_problem* pr, int32_t B, const doubl
 struct SlabPipe {
     rg_ctx* ctx; int nslab, per; std::vector<cudaEvent_t> ev;
     SlabPipe(rg_ctx* c, int B) : ctx(c) {
-        nslab = std::max(1, std::min(c->host_slabs, B / 2048));
+        nslab = std::max(1, std::min(c->host_slabs, B / std::max(1, c->host_slab_min)));
         per = (B + nslab - 1) / nslab;
         nslab = (B + per - 1) / per;
         ev.resize(2 * nslab);

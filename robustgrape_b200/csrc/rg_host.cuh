@@ -26,7 +26,8 @@ struct rg_ctx {
     size_t ws_limit = (size_t)64 << 30;
     // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
-    int host_slabs = 4;                               // RG_HOST_SLABS (upper bound; slabs hold >= 2048 pulses)
+    int host_slabs = 4;                               // RG_HOST_SLABS (upper bound on the number of slabs)
+    int host_slab_min = 2048;                         // RG_HOST_SLAB_MIN (smallest slab, pulses)
     cudaStream_t s_peer[2] = {nullptr, nullptr};      // side streams of rg_gather_to_peers (created on first use)
     cudaEvent_t ev_src = nullptr, ev_peer_join = nullptr, ev_gather[2] = {nullptr, nullptr};
     bool gather_pending[2] = {false, false};
