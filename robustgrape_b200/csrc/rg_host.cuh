@@ -130,6 +130,12 @@ static inline Plan make_plan(const rg_problem* pr, int B) {
     // short enough to expose (pulse, chunk) parallelism for small batches
     const long long lmin = (pl.slab >= 64) ? 16 : 4;
     int L = (int)std::max<long long>(lmin, std::min<long long>(32, P.N / std::max<long long>(1, want_nc)));
+    // measured on B200 with the thread-per-chunk sweeps (C4, N = 1000): 1024 pulses: L = 32 beats 16 (0.249 vs 0.289 ms),
+    // 8192 pulses: L = 50 beats 32 (1.42 vs 1.45 ms) -- longer chunks shorten the sequential k_scan
+    if (pr->tri_ok && !pr->force_group && !pr->force_group_sweeps) {
+        if (pl.slab >= 4096) L = 50;
+        else if (pl.slab >= 512) L = 32;
+    }
     if (pr->chunk_override > 0) L = pr->chunk_override;
     L = std::min(L, P.N);
     pl.L = L;
@@ -302,7 +308,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     // ---- K2
     {
         const int gs = k2_group_stride(D);
-        int wpc = 2;
+        int wpc = RG_SCAN_WPC;
         while (wpc > 1 && (size_t)wpc * G * gs * cb > 200 * 1024) wpc >>= 1;
         const size_t smem = (size_t)wpc * G * gs * cb;
         int rc = set_smem(ctx, k_scan<D>, smem);

@@ -45,7 +45,12 @@ __host__ __device__ inline int k1_group_stride(int D, int nterms, int ne) {
 __host__ __device__ inline int k1b_group_stride(int D, int nterms) { return rg_odd(5 * D * D + 4 * nterms); }
 __host__ __device__ inline int kagg_group_stride(int D, int ne) { return rg_odd((2 * (1 + ne) + ne) * D * D + 1); }
 __host__ __device__ inline int kmat_group_stride(int D, int nload) { return rg_odd((nload + 2) * D * D + 1); }
-#define RG_SCAN_RING 4
+#ifndef RG_SCAN_RING
+#define RG_SCAN_RING 2          // cp.async ring depth; 2 + one warp per CTA fits 5 CTAs/SM (2 waves at B = 8192), measured 0.134 vs 0.157 ms
+#endif
+#ifndef RG_SCAN_WPC
+#define RG_SCAN_WPC 1          // warps per CTA of k_scan
+#endif
 __host__ __device__ inline int k2_group_stride(int D) { return rg_odd((14 + 2 * RG_SCAN_RING) * D * D + D + 1); }
 __host__ __device__ inline int k3_group_stride(int D, int nload) { return rg_odd(2 * nload * D * D + D + 1); }
 

@@ -431,8 +431,11 @@ def test_device_pointer_entry_point_matches_host_entry_point(gpu_ctx):
         dp.cost_and_grad_batch_dev(B, nx, dX.data_ptr(), [1e-4], dc.data_ptr(), dg.data_ptr())
         dp.ctx.synchronize()
         dp.ctx.set_stream(0)
-    assert np.array_equal(dc.cpu().numpy(), cost_h)
-    assert np.array_equal(dg.cpu().numpy().reshape(B, nx).T, grad_h)
+    # the host path evaluates 2050-pulse slabs, the device path one 4100-pulse slab: the planner picks different chunk
+    # lengths for them, so the two agree to rounding (test_chunk_length_independence: 1e-11), not bit for bit
+    assert np.allclose(dc.cpu().numpy(), cost_h, rtol=0, atol=1e-12)
+    g_dev = dg.cpu().numpy().reshape(B, nx).T
+    assert np.abs(g_dev - grad_h).max() <= 1e-11 * max(1.0, np.abs(grad_h).max())
 
 
 @pytest.mark.parametrize("mode", [0, 1])
