@@ -617,6 +617,7 @@ k_chunk_agg_t(const DevProblem P, int B, int L, int nc, const cplx* __restrict__
             M wl; wl.zero();
             for (int k = k0; k < k1; ++k) {
                 const cplx* wsk = wsb + (size_t)k * PT::nnz;
+                if (k + 1 < k1) { M::prefetch(wsk + PT::nnz); M::prefetch(wsk + PT::nnz + (size_t)(1 + nv + e) * objS); }
                 M u, de; u.load(wsk); de.load(wsk + (size_t)(1 + nv + e) * objS);
                 M wn; pmat_mul<D, CM, false, false>(wn, u, wl); pmat_mul<D, CM, false, true>(wn, de, q);
                 M qn; pmat_mul<D, CM, false, false>(qn, u, q);
