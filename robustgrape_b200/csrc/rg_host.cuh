@@ -133,8 +133,21 @@ static inline Plan make_plan(const rg_problem* pr, int B) {
     // measured on B200 with the thread-per-chunk sweeps (C4, N = 1000): 1024 pulses: L = 32 beats 16 (0.249 vs 0.289 ms),
     // 8192 pulses: L = 50 beats 32 (1.42 vs 1.45 ms) -- longer chunks shorten the sequential k_scan
     if (pr->tri_ok && !pr->force_group && !pr->force_group_sweeps) {
-        if (pl.slab >= 4096) L = 50;
-        else if (pl.slab >= 512) L = 32;
+        if (pl.slab >= 2048) {
+            // Several waves of thread-per-chunk CTAs: pick the chunk count that wastes least in the last wave of the gradient
+            // sweep (2 CTAs/SM) and of the aggregate sweep (3 CTAs/SM) while keeping the sequential k_scan short. Weights are
+            // the measured C4 kernel times (ms at 8192 pulses); the model reproduces the measured ranking of L = 32 ... 84
+            // (L = 77, 13 chunks: 1.36 ms; L = 50: 1.42 ms; L = 32: 1.45 ms).
+            const double per_wave_g = 2.0 * pr->ctx->sm_count * 128, per_wave_a = 3.0 * pr->ctx->sm_count * 128;
+            double best = 1e300;
+            for (int cand = 32; cand <= 96 && cand <= P.N; ++cand) {
+                const int ncc = (P.N + cand - 1) / cand;
+                if (cand > 32 && (P.N + cand - 2) / (cand - 1) == ncc) continue;      // same chunk count as a shorter chunk
+                const double wg = (double)pl.slab * ncc / per_wave_g, wa = (double)pl.slab * ncc / per_wave_a;
+                const double cost = 0.43 * std::ceil(wg) / wg + 0.22 * std::ceil(wa) / wa + 0.0047 * ncc;
+                if (cost < best) { best = cost; L = cand; }
+            }
+        } else if (pl.slab >= 512) L = 32;
     }
     if (pr->chunk_override > 0) L = pr->chunk_override;
     L = std::min(L, P.N);
