@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import os
+import re
 import shutil
 import subprocess
 from pathlib import Path
@@ -26,12 +27,33 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(src, seen=None):
+    """The translation unit and every project header it includes (recursively)."""
+    seen = set() if seen is None else seen
+    src = src.resolve()
+    if src in seen or not src.exists():
+        return seen
+    seen.add(src)
+    for inc in _INC.findall(src.read_text()):
+        _deps((src.parent / inc), seen)
+    return seen
+
+
+def _stale(src, obj):
+    if not obj.exists():
+        return True
+    t = obj.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in _deps(src))
+
+
 def needs_build():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [ROOT.parent / "include" / "robustgrape_b200.h"]
-    return any(p.stat().st_mtime > t for p in deps)
+    return any(p.stat().st_mtime > t for src in sources() for p in _deps(src))
 
 
 def build_cuda(force=False, verbose=False):
@@ -43,13 +65,16 @@ def build_cuda(force=False, verbose=False):
     OBJ_DIR.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     procs = []
+    objs = []
     for src in sources():
         obj = OBJ_DIR / (src.stem + ".o")
+        if not force and not _stale(src, obj):      # per-translation-unit incremental build
+            objs.append(str(obj))
+            continue
         cmd = [nvcc, *COMPILE_FLAGS, "-c", "-o", str(obj), str(src)]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs = []
     for src, obj, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

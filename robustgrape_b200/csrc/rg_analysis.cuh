@@ -212,12 +212,14 @@ k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restr
     __shared__ cplx sS[NS][DD], sT[NS][DD];
     __shared__ cplx mS[DD], mT[DD];
     const int f = blockIdx.x, e = blockIdx.y;
-    const int tid = threadIdx.x, el = tid % DD, sl = tid / DD;
+    const int tid = threadIdx.x;
     const int n = first + f;
     const double w = M > 0 ? 0.0 : freqs[n];
     const double wdt = w * P.dt;
-    cplx s = cmk(0, 0), t = cmk(0, 0);
-    if (sl < NS) {
+    // (slice, element) pairs are strided over the block: d*d may exceed the block size (d = 12, 16)
+    for (int idx = tid; idx < NS * DD; idx += blockDim.x) {
+        const int el = idx % DD, sl = idx / DD;
+        cplx s = cmk(0, 0), t = cmk(0, 0);
         const cplx* Oe = O + (size_t)e * P.N * DD;
         for (int j = sl; j < P.N; j += NS) {
             double sn, cs;
@@ -234,15 +236,15 @@ k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restr
         sS[sl][el] = s; sT[sl][el] = t;
     }
     __syncthreads();
-    if (tid < DD) {
+    for (int el = tid; el < DD; el += blockDim.x) {
         cplx a = cmk(0, 0), b = cmk(0, 0);
-        for (int q = 0; q < NS; ++q) { a = cadd(a, sS[q][tid]); b = cadd(b, sT[q][tid]); }
+        for (int q = 0; q < NS; ++q) { a = cadd(a, sS[q][el]); b = cadd(b, sT[q][el]); }
         if (shift) {
             double sn, cs;
             sincos(wdt, &sn, &cs);
             b = cmul(b, cmk(cs, sn));
         }
-        mS[tid] = a; mT[tid] = b;
+        mS[el] = a; mT[el] = b;
     }
     __syncthreads();
     if (tid == 0) {

@@ -6,12 +6,12 @@
 
 #define RG_DECL_DIM(D) extern const DimOps rg_ops_d##D;
 RG_DECL_DIM(2) RG_DECL_DIM(3) RG_DECL_DIM(4) RG_DECL_DIM(5) RG_DECL_DIM(6) RG_DECL_DIM(7) RG_DECL_DIM(8) RG_DECL_DIM(9)
-RG_DECL_DIM(10) RG_DECL_DIM(12) RG_DECL_DIM(16)
+RG_DECL_DIM(10)
 const DimOps* rg_dim_ops(int d) {
     switch (d) {
     case 2: return &rg_ops_d2; case 3: return &rg_ops_d3; case 4: return &rg_ops_d4; case 5: return &rg_ops_d5;
     case 6: return &rg_ops_d6; case 7: return &rg_ops_d7; case 8: return &rg_ops_d8; case 9: return &rg_ops_d9;
-    case 10: return &rg_ops_d10; case 12: return &rg_ops_d12; case 16: return &rg_ops_d16;
+    case 10: return &rg_ops_d10;
     default: return nullptr;
     }
 }
@@ -266,8 +266,9 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_GROUP_SWEEPS")) pr->force_group_sweeps = atoi(s);
     if (const char* s = getenv("RG_FUSED_AGG")) pr->fused_agg = atoi(s);
     if (const char* s = getenv("RG_SEQ_ANALYSIS")) pr->force_sequential_analysis = atoi(s);
+    if (const char* s = getenv("RG_WS")) pr->force_ws = atoi(s);
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
-    if (P.hermitian && d <= 5 && P.nterms <= RG_T_MAX_TERMS) {
+    if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS) {
         const int npos = d * (d + 1) / 2;
         std::vector<std::vector<std::pair<int, std::pair<double, double>>>> lists(npos);
         std::vector<double> colw((size_t)std::max(1, P.nterms) * d, 0.0);
@@ -435,8 +436,11 @@ extern "C" int rg_fidelity_and_derivatives_batch(rg_problem* pr, int32_t B, cons
     CU(ctx, cudaStreamSynchronize(ctx->s_out));
     int rcs = rg_ctx_synchronize(ctx);
     if (rcs == RG_ERR_NORM && pr->tri_ok && !pr->force_group) {      // fast path out of range: general kernels square
+        // per call: the next call tries the fast path again (a later batch may be in range)
         pr->force_group = 1;
-        return rg_fidelity_and_derivatives_batch(pr, B, X, F, F_dx, F_d2err, F_d2err_dx);
+        const int rc2 = rg_fidelity_and_derivatives_batch(pr, B, X, F, F_dx, F_d2err, F_d2err_dx);
+        pr->force_group = 0;
+        return rc2;
     }
     return rcs;
 }
@@ -472,7 +476,9 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
     int rcs = rg_ctx_synchronize(ctx);
     if (rcs == RG_ERR_NORM && pr->tri_ok && !pr->force_group) {
         pr->force_group = 1;
-        return rg_cost_and_grad_batch(pr, B, X, err_coeff, cost, grad);
+        const int rc2 = rg_cost_and_grad_batch(pr, B, X, err_coeff, cost, grad);
+        pr->force_group = 0;
+        return rc2;
     }
     return rcs;
 }

@@ -1,4 +1,3 @@
-// Instantiates the kernels and launch templates for ndim = 10, 12 (see rg_host.cuh).
+// Instantiates the kernels and launch templates for ndim = 10 (see rg_host.cuh).
 #include "rg_host.cuh"
 RG_DEFINE_DIM(10)
-RG_DEFINE_DIM(12)

@@ -76,6 +76,8 @@ struct rg_problem {
                                   // product issues 5 x 64 DFMA warp-instructions with most lanes idle)
     int force_group_sweeps = 0;   // RG_GROUP_SWEEPS=1: group (shared-memory) versions of k_chunk_agg / k_grad
     int force_sequential_analysis = 0;   // RG_SEQ_ANALYSIS=1: time-sequential interaction-operator kernel
+    int force_ws = 0;             // RG_WS=1: step-matrix workspace path even where the workspace-free block-2 path applies
+    int b2_agg_ctas = 0, b2_grad_ctas = 0;   // resident CTAs/SM of the block-2 sweeps (occupancy query, cached)
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
     double tri_density = 1.0;
@@ -103,6 +105,16 @@ struct rg_problem {
     } while (0)
 
 
+// ---- workspace-free block-2 path (rg_block2.cu): closed-form 2 x 2 block propagators recomputed inside the sweeps
+int rg_b2_pattern(const rg_problem* pr);          // 0 = not eligible, else the instantiated pattern
+int rg_b2_launch_agg(rg_problem* pr, const DevProblem& P, int B, int L, int nc, const double* dX);
+int rg_b2_launch_grad(rg_problem* pr, const DevProblem& P, int B, int L, int nc, const double* dX, double* out0, double scale0);
+int rg_b2_launch_grad_err(rg_problem* pr, const DevProblem& P, int B, int L, int nc, const double* dX, double* out1);
+void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas);
+static inline bool rg_use_b2(const rg_problem* pr) {
+    return !pr->force_group && !pr->force_dense && !pr->force_group_sweeps && !pr->fused_agg && rg_b2_pattern(pr) != 0;
+}
+
 // ---- per-dimension operations table (defined by RG_DEFINE_DIM in rg_dims_*.cu) --------------------------
 struct Plan;
 struct DimOps {
@@ -117,9 +129,34 @@ const DimOps* rg_dim_ops(int d);
 // ------------------------------------------------------------------------------------------
 struct Plan { int L, nc, slab; };
 
-static inline Plan make_plan(const rg_problem* pr, int B) {
+static inline Plan make_plan(rg_problem* pr, int B) {
     const DevProblem& P = pr->dp;
     Plan pl;
+    if (rg_use_b2(pr)) {
+        // Workspace-free path: nothing of size N is stored, so the whole batch is one slab.  The chunk length trades the
+        // tail of the last wave of the two thread-per-(pulse, chunk) sweeps against the sequential chunk scan:
+        //   cost(L) = L * (ceil(items / cap_grad) + 0.5 * ceil(items / cap_agg)) + 2 * nc * ceil(B / scan_cap)
+        // in units of one sweep step; capacities come from occupancy queries of the kernels that will run, the aggregate
+        // sweep does about half the work of the gradient sweep per step, and one scan step costs about two sweep steps.
+        if (!pr->b2_grad_ctas) rg_b2_occupancy(pr, &pr->b2_agg_ctas, &pr->b2_grad_ctas);
+        const double cap_g = (double)pr->ctx->sm_count * pr->b2_grad_ctas * 128, cap_a = (double)pr->ctx->sm_count * pr->b2_agg_ctas * 128;
+        const double scan_cap = (double)pr->ctx->sm_count * 5 * (32 / P.d);
+        pl.slab = B;
+        int L = std::min(P.N, 32);
+        double best = 1e300;
+        for (int cand = 4; cand <= 128 && cand <= P.N; ++cand) {
+            const int ncc = (P.N + cand - 1) / cand;
+            if (cand > 4 && (P.N + cand - 2) / (cand - 1) == ncc) continue;          // same chunk count as a shorter chunk
+            const double items = (double)B * ncc;
+            const double cost = cand * (std::ceil(items / cap_g) + 0.5 * std::ceil(items / cap_a)) + 2.0 * ncc * std::ceil(B / scan_cap);
+            if (cost < best) { best = cost; L = cand; }
+        }
+        if (pr->chunk_override > 0) L = pr->chunk_override;
+        L = std::max(1, std::min(L, P.N));
+        pl.L = L;
+        pl.nc = (P.N + L - 1) / L;
+        return pl;
+    }
     const size_t per_pulse = (size_t)P.N * P.nstore * P.d * P.d * sizeof(cplx);
     size_t slab = std::max<size_t>(1, pr->ctx->ws_limit / std::max<size_t>(per_pulse, 1));
     pl.slab = (int)std::min<size_t>(slab, (size_t)B);
@@ -130,21 +167,17 @@ static inline Plan make_plan(const rg_problem* pr, int B) {
     // short enough to expose (pulse, chunk) parallelism for small batches
     const long long lmin = (pl.slab >= 64) ? 16 : 4;
     int L = (int)std::max<long long>(lmin, std::min<long long>(32, P.N / std::max<long long>(1, want_nc)));
-    // measured on B200 with the thread-per-chunk sweeps (C4, N = 1000): 1024 pulses: L = 32 beats 16 (0.249 vs 0.289 ms),
-    // 8192 pulses: L = 50 beats 32 (1.42 vs 1.45 ms) -- longer chunks shorten the sequential k_scan
-    if (pr->tri_ok && !pr->force_group && !pr->force_group_sweeps) {
+    if (pr->tri_ok && P.d <= 5 && !pr->force_group && !pr->force_group_sweeps) {
+        // thread-per-chunk sweeps over the step-matrix workspace (structured d <= 5 problems outside the block-2 path):
+        // longer chunks shorten the sequential k_scan; 2 (gradient) and 3 (aggregate) resident CTAs/SM of 128 threads
         if (pl.slab >= 2048) {
-            // Several waves of thread-per-chunk CTAs: pick the chunk count that wastes least in the last wave of the gradient
-            // sweep (2 CTAs/SM) and of the aggregate sweep (3 CTAs/SM) while keeping the sequential k_scan short. Weights are
-            // the measured C4 kernel times (ms at 8192 pulses); the model reproduces the measured ranking of L = 32 ... 84
-            // (L = 77, 13 chunks: 1.36 ms; L = 50: 1.42 ms; L = 32: 1.45 ms).
             const double per_wave_g = 2.0 * pr->ctx->sm_count * 128, per_wave_a = 3.0 * pr->ctx->sm_count * 128;
             double best = 1e300;
             for (int cand = 32; cand <= 96 && cand <= P.N; ++cand) {
                 const int ncc = (P.N + cand - 1) / cand;
                 if (cand > 32 && (P.N + cand - 2) / (cand - 1) == ncc) continue;      // same chunk count as a shorter chunk
                 const double wg = (double)pl.slab * ncc / per_wave_g, wa = (double)pl.slab * ncc / per_wave_a;
-                const double cost = 0.43 * std::ceil(wg) / wg + 0.22 * std::ceil(wa) / wa + 0.0047 * ncc;
+                const double cost = 2.0 * std::ceil(wg) / wg + std::ceil(wa) / wa + 0.02 * ncc;
                 if (cost < best) { best = cost; L = cand; }
             }
         } else if (pl.slab >= 512) L = 32;
@@ -213,7 +246,8 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     if (!pr->has_target) RG_FAIL(ctx, RG_ERR_INVALID, "problem has no target/projector: fidelity entry points unavailable");
 
     const size_t cb = sizeof(cplx);
-    if (pr->ws.ensure((size_t)B * P.N * P.nstore * WSM * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
+    const bool b2 = rg_use_b2(pr);
+    if (pr->ws.ensure(b2 ? 16 : (size_t)B * P.N * P.nstore * WSM * cb) || pr->Qb.ensure((size_t)B * nc * DD * cb) ||
         pr->Wlb.ensure(std::max<size_t>(16, (size_t)B * nc * ne * DD * cb)) || pr->Cb.ensure((size_t)B * nc * DD * cb) ||
         pr->Wb.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) || pr->Gb.ensure((size_t)B * nc * DD * cb) ||
         pr->G1b.ensure(std::max<size_t>(16, (size_t)B * ne * nc * DD * cb)) ||
@@ -241,7 +275,11 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
     constexpr bool kSparseThread = (PID != PAT_FULL) && (Pat<D, CMS>::nnz <= 12);   // state fits one thread's registers
     const bool fast = kThreadOK && pr->tri_ok && !pr->force_group;
     if (!fast && PID != PAT_FULL) RG_FAIL(ctx, RG_ERR_INVALID, "internal: structural pattern without the fast path");
-    if (fast) {
+    if (b2) {
+        // workspace-free: chunk aggregates from recomputed closed-form block propagators (rg_block2.cuh)
+        int rc = rg_b2_launch_agg(pr, P, B, L, nc, dX);
+        if (rc) return rc;
+    } else if (fast) {
         // Hermitian fast path: one thread per time step, triangles in registers; aggregates in a second kernel.
         constexpr int DT = kThreadOK ? D : 2;
         constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
@@ -296,7 +334,9 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
                                                        pr->Wlb.as<cplx>(), ctx->d_status);
     }
     // ---- K1b: mixed second differences (only needed for the sensitivity gradient)
-    if (ne > 0 && want_grad && P.nvar > 0 && fast && PID != PAT_FULL) {
+    if (b2) {
+        // mixed second differences are recomputed inside the sensitivity-gradient sweep
+    } else if (ne > 0 && want_grad && P.nvar > 0 && fast && PID != PAT_FULL) {
         // structured fast path: thread per step, four triangles in registers
         constexpr int DT = kThreadOK ? D : 2;
         constexpr unsigned UM = tri_mask_of<DT, (kThreadOK ? PID : PAT_FULL)>();
@@ -339,8 +379,14 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         // ---- K3: backward gradient sweeps (fidelity role, then one role per error source)
         const long long items = (long long)B * nc;
         bool grad_done = false, graderr_done = false;
+        if (b2) {
+            int rc = rg_b2_launch_grad(pr, P, B, L, nc, dX, iFdx, sign0 * P.inv_eps / DD1);
+            if (rc) return rc;
+            if (ne > 0) { rc = rg_b2_launch_grad_err(pr, P, B, L, nc, dX, iF2dx); if (rc) return rc; }
+            grad_done = graderr_done = true;
+        }
         if constexpr (kSparseThread) {
-            if (fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
+            if (!grad_done && fast && !pr->force_group_sweeps && pr->costate_in_pattern) {
                 {
                     KTimer kt(ctx, RG_K_GRAD);
                     k_grad_t<D, CMS><<<(int)((items + 127) / 128), 128, 0, st>>>(P, B, L, nc, pr->ws.as<cplx>(), pr->Cb.as<cplx>(),
@@ -409,6 +455,7 @@ template <int D>
 static int dim_run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mode, const double* d_coeff,
                         double* dF, double* dFdx, double* dF2, double* dF2dx, bool want_grad) {
     const bool fast = pr->tri_ok && !pr->force_group && !pr->force_dense;
+    if (rg_use_b2(pr)) return run_slab<D, PAT_FULL>(pr, B, pl, dX, mode, d_coeff, dF, dFdx, dF2, dF2dx, want_grad);
     if constexpr (D == 5) {
         if (fast) {
             if ((pr->tri_union & ~tri_mask_of<5, PAT_M5_DRIVE>()) == 0)

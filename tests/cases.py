@@ -89,6 +89,14 @@ def golden_cases():
     cases["cz7_e2_N10"] = (fp, random_pulse(fp, 1, 14))
     fp = detuned_problem(9, 1.1, ("amp", "freq"))
     cases["detuned_p2_a2_e2_N9"] = (fp, random_pulse(fp, 2, 15))
+    # BASELINE.json configs[1] at full size: examples/ar_cz.jl (N = 200, t0 = 14.32, amplitude error)
+    fp = cz_problem(200, 14.32, ("amp",))
+    cases["cz5_C2_e1_N200"] = (fp, random_pulse(fp, 1, 21))
+    # detuned 5- and 7-level models (diagonal terms inside the 2 x 2 blocks), two error sources
+    fp = cz_problem(31, 7.613 * 31 / 100, ("freq", "amp"), delta=0.37, eps=0.02)
+    cases["cz5_detuned_e2_N31"] = (fp, random_pulse(fp, 1, 22))
+    fp = cz_problem(19, 7.613 * 19 / 60, ("amp", "freq"), model="full_blockaded", delta=-0.21)
+    cases["cz7_detuned_e2_N19"] = (fp, random_pulse(fp, 1, 23))
     return cases
 
 

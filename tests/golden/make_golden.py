@@ -22,7 +22,10 @@ from cases import golden_cases  # noqa: E402
 from oracle import exact_oracle as eo, reference_oracle as ro  # noqa: E402
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
     for name, (fp, x) in golden_cases().items():
+        if only and name not in only:
+            continue
         e = eo.calculate_fidelity_and_derivatives(fp, x)
         a = ro.calculate_fidelity_and_derivatives(fp, x)
         out = {"x": x}
