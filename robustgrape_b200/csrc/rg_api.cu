@@ -267,6 +267,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_FUSED_AGG")) pr->fused_agg = atoi(s);
     if (const char* s = getenv("RG_SEQ_ANALYSIS")) pr->force_sequential_analysis = atoi(s);
     if (const char* s = getenv("RG_WS")) pr->force_ws = atoi(s);
+    if (const char* s = getenv("RG_B2")) pr->force_b2 = atoi(s);
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
     if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS) {
         const int npos = d * (d + 1) / 2;

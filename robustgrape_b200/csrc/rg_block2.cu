@@ -2,6 +2,7 @@
 // unroll into long straight-line kernels, and nothing here depends on the per-dimension group kernels.
 #include "rg_host.cuh"
 #include "rg_block2.cuh"
+#include "rg_fusedq.cuh"
 
 // Patterns instantiated ahead of time (upper-triangle bit = k(k+1)/2 + i):
 //   d = 5 symmetric-blockaded model (src/RydbergTools.jl:31-39): drive (1,3),(2,4) [+ Rydberg diagonal (3,3),(4,4)]
@@ -92,4 +93,52 @@ void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas) {
     default: break;
     }
     *agg_ctas = std::max(1, a); *grad_ctas = std::max(1, g);
+}
+
+// ---- one-launch fused quaternion path (rg_fusedq.cuh): patterns without diagonal terms
+static_assert(b2_quat(5, B2_M5_DRIVE) && b2_quat(7, B2_M7_DRIVE) && !b2_quat(5, B2_M5_FULL), "quaternion eligibility");
+int rg_fq_pattern(const rg_problem* pr) {
+    const int p = rg_b2_pattern(pr);
+    return (p == 1 || p == 3) ? p : 0;
+}
+template <int D, unsigned UM>
+static int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
+                     double scale0, double scale0T, int do_grad) {
+    rg_ctx* ctx = pr->ctx;
+    const size_t smem = fq_smem_bytes(D, b2_nblocks(D, UM), P.nterms, pr->tri.nent);
+    if (!pr->fq_ctas[0]) {
+        int rc = set_smem(ctx, k_fused_q<D, UM, false>, smem); if (rc) return rc;
+        rc = set_smem(ctx, k_fused_q<D, UM, true>, smem); if (rc) return rc;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[0], k_fused_q<D, UM, false>, 128, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[1], k_fused_q<D, UM, true>, 128, smem);
+        pr->fq_ctas[0] = std::max(1, pr->fq_ctas[0]); pr->fq_ctas[1] = std::max(1, pr->fq_ctas[1]);
+    }
+    // warps per pulse: cost = waves * (sweep steps per lane + fixed scan/algebra overhead of ~24 sweep steps)
+    const double cap = (double)ctx->sm_count * pr->fq_ctas[err_role ? 1 : 0];
+    int wpp = 1; double best = 1e300;
+    for (int w = 1; w <= 4; w <<= 1) {
+        const int Lw = (P.N + 32 * w - 1) / (32 * w);
+        const double ctas = std::ceil((double)B * w / 4.0) * (err_role ? P.e : 1);
+        const double cost = std::ceil(ctas / cap) * (Lw + 24.0);
+        if (cost < best) { best = cost; wpp = w; }
+    }
+    if (pr->chunk_override > 0) wpp = std::max(1, std::min(4, pr->chunk_override >= 4 ? 4 : pr->chunk_override));
+    if (wpp == 3) wpp = 2;
+    const int L = (P.N + 32 * wpp - 1) / (32 * wpp);
+    const int ppc = 4 / wpp;
+    dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? P.e : 1);
+    KTimer kt(ctx, err_role ? RG_K_GRAD_ERR : RG_K_GRAD);
+    if (err_role)
+        k_fused_q<D, UM, true><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+    else
+        k_fused_q<D, UM, false><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+    return RG_OK;
+}
+int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
+                 double scale0, double scale0T, int do_grad) {
+    switch (rg_fq_pattern(pr)) {
+    case 1: return launch_fq<5, B2_M5_DRIVE>(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad);
+    case 3: return launch_fq<7, B2_M7_DRIVE>(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad);
+    default: pr->ctx->err = "internal: fused quaternion path without an eligible pattern"; return RG_ERR_INVALID;
+    }
 }

@@ -1,0 +1,387 @@
+// rg_fusedq.cuh -- one-launch fused evaluation for block-2 Hamiltonians without diagonal terms (resonant drives: the
+// 5-/7-level Rydberg CZ models with delta = 0 and amplitude-type error sources; BASELINE.json configs 1, 2 and 4).
+//
+// Algebra.  With no diagonal term every 2 x 2 block of every step propagator is  exp([[0, w], [-conj w, 0]]) =
+// [[C, wS], [-conj(w) S, C]] -- a *quaternion* [[a, b], [-conj b, conj a]] -- and so is every finite difference of it
+// (quaternions are closed under sums and products).  Hence all forward states (C_k, W_k = dC_k/derr) are quaternions:
+// 2 complex numbers per block instead of 4, 16 real multiplications per product instead of 32.  The co-states
+// G = K B are not, but they are only ever used as Re tr(G X) with X a quaternion, and for M = q1 + i q2 (q1, q2
+// quaternions) Re tr(M X) = tr(q1 X): only the quaternion projection q1 = proj(M) of the co-state seed matters, and
+// proj(K B) = proj(K) B.  So the whole sweep runs in quaternion arithmetic; the fidelity algebra itself (general
+// projector / target, src/FidelityCalculations.jl:47-114) is done once per pulse on dense d x d matrices.
+//
+// Mapping.  One pulse = `wpp` warps of one CTA (wpp = 1, 2 or 4); lane t of the pulse owns the chunk of L = ceil(N / 32 wpp)
+// consecutive time steps [tL, (t+1)L).
+//   1. forward sweep over the chunk: Q_t = U_last ... U_first  (error role: also V_t = dQ_t/derr), propagators recomputed
+//      from x_k in closed form (rg_block2.cuh);
+//   2. inclusive ordered scan of (Q, V) over the pulse's lanes with warp shuffles (+ shared memory across warps): state at
+//      the end of every chunk, and C_N, W_N at the last lane;
+//   3. D lanes of the pulse run the fidelity algebra on C_N (or E = W_N/eps) in shared memory -> F (or F_d2err), seed K;
+//   4. every lane forms its co-states from the totals: B_t = C_N P_t^dag (suffix product by unitarity),
+//      dB_t = (W_N - B_t V_t) P_t^dag, G = proj(K) B_t, H' = proj(K') dB_t;
+//   5. backward sweep over the chunk: rewind the forward state with U_k^dag, contract with the recomputed differences,
+//      advance the co-states; gradient entries go straight to the output, x_add entries are reduced in the CTA.
+// Nothing of size N touches HBM except x (read twice) and the gradient (written once); one launch per role.
+#pragma once
+#include "rg_block2.cuh"
+
+__host__ __device__ constexpr int b2_nblocks(int d, unsigned tri) {
+    int n = 0;
+    for (int l = 0; l < d; ++l)
+        if (b2_partner(d, tri, l) > l) ++n;
+    return n;
+}
+__host__ __device__ constexpr int b2_block_lo(int d, unsigned tri, int n) {
+    int c = 0;
+    for (int l = 0; l < d; ++l)
+        if (b2_partner(d, tri, l) > l) { if (c == n) return l; ++c; }
+    return -1;
+}
+// quaternion-eligible: blocks of <= 2 levels and no diagonal position anywhere in the mask
+__host__ __device__ constexpr bool b2_quat(int d, unsigned tri) {
+    if (!b2_eligible(d, tri)) return false;
+    for (int l = 0; l < d; ++l)
+        if ((tri >> (l * (l + 1) / 2 + l)) & 1u) return false;
+    return true;
+}
+
+template <int NB> struct QS { cplx a[NB], b[NB]; };          // one quaternion [[a, b], [-conj b, conj a]] per block
+// (lo, hi) levels of block n as constants that fold after unrolling (at most 4 two-level blocks for d <= 8)
+template <int D, unsigned UMASK> struct QBlk {
+    static constexpr int NB = b2_nblocks(D, UMASK);
+    static constexpr int l0 = b2_block_lo(D, UMASK, 0), l1 = b2_block_lo(D, UMASK, 1), l2 = b2_block_lo(D, UMASK, 2), l3 = b2_block_lo(D, UMASK, 3);
+    static constexpr int h0 = l0 >= 0 ? b2_partner(D, UMASK, l0 >= 0 ? l0 : 0) : -1, h1 = l1 >= 0 ? b2_partner(D, UMASK, l1 >= 0 ? l1 : 0) : -1,
+                         h2 = l2 >= 0 ? b2_partner(D, UMASK, l2 >= 0 ? l2 : 0) : -1, h3 = l3 >= 0 ? b2_partner(D, UMASK, l3 >= 0 ? l3 : 0) : -1;
+    __device__ static __forceinline__ int lo(int n) { return n == 0 ? l0 : n == 1 ? l1 : n == 2 ? l2 : l3; }
+    __device__ static __forceinline__ int hi(int n) { return n == 0 ? h0 : n == 1 ? h1 : n == 2 ? h2 : h3; }
+};
+
+template <int NB> __device__ __forceinline__ void qs_identity(QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { q.a[n] = cmk(1.0, 0.0); q.b[n] = cmk(0.0, 0.0); }
+}
+template <int NB> __device__ __forceinline__ void qs_zero(QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { q.a[n] = cmk(0.0, 0.0); q.b[n] = cmk(0.0, 0.0); }
+}
+// r (+)= p q :  (pa qa - pb conj(qb), pa qb + pb conj(qa))
+template <int NB, bool ACC = false>
+__device__ __forceinline__ void qs_mul(QS<NB>& r, const QS<NB>& p, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = ACC ? r.a[n] : cmk(0.0, 0.0), b = ACC ? r.b[n] : cmk(0.0, 0.0);
+        cfma(a, p.a[n], q.a[n]); cfma(a, cmk(-p.b[n].x, -p.b[n].y), cconj(q.b[n]));
+        cfma(b, p.a[n], q.b[n]); cfma(b, p.b[n], cconj(q.a[n]));
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+// r = p^dag q :  p^dag = (conj pa, -pb)
+template <int NB>
+__device__ __forceinline__ void qs_adjmul(QS<NB>& r, const QS<NB>& p, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = cmk(0.0, 0.0), b = cmk(0.0, 0.0);
+        cfma_conj(a, p.a[n], q.a[n]); cfma(a, p.b[n], cconj(q.b[n]));
+        cfma_conj(b, p.a[n], q.b[n]); cfma(b, cmk(-p.b[n].x, -p.b[n].y), cconj(q.a[n]));
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+// r = p q^dag :  q^dag = (conj qa, -qb)  ->  (pa conj(qa) + pb conj(qb), -pa qb + pb qa)
+template <int NB>
+__device__ __forceinline__ void qs_muladj(QS<NB>& r, const QS<NB>& p, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = cmk(0.0, 0.0), b = cmk(0.0, 0.0);
+        cfma(a, p.a[n], cconj(q.a[n])); cfma(a, p.b[n], cconj(q.b[n]));
+        cfma(b, cmk(-p.a[n].x, -p.a[n].y), q.b[n]); cfma(b, p.b[n], q.a[n]);
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+template <int NB> __device__ __forceinline__ void qs_sub(QS<NB>& r, const QS<NB>& p, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { r.a[n] = csub(p.a[n], q.a[n]); r.b[n] = csub(p.b[n], q.b[n]); }
+}
+// Re tr(g t) over all blocks = sum 2 Re(ga ta - gb conj(tb))
+template <int NB> __device__ __forceinline__ double qs_retrace(const QS<NB>& g, const QS<NB>& t) {
+    double s = 0.0;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        s = fma(g.a[n].x, t.a[n].x, s); s = fma(-g.a[n].y, t.a[n].y, s);
+        s = fma(-g.b[n].x, t.b[n].x, s); s = fma(-g.b[n].y, t.b[n].y, s);
+    }
+    return 2.0 * s;
+}
+template <int NB> __device__ __forceinline__ QS<NB> qs_shfl_up(const QS<NB>& q, int delta) {
+    QS<NB> r;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        r.a[n].x = __shfl_up_sync(0xffffffffu, q.a[n].x, delta); r.a[n].y = __shfl_up_sync(0xffffffffu, q.a[n].y, delta);
+        r.b[n].x = __shfl_up_sync(0xffffffffu, q.b[n].x, delta); r.b[n].y = __shfl_up_sync(0xffffffffu, q.b[n].y, delta);
+    }
+    return r;
+}
+
+// Quaternion view of a step propagator and its differences (slots of the jet)
+template <int D, unsigned UMASK, int O>
+struct QBlocks {
+    static constexpr int NB = b2_nblocks(D, UMASK);
+    template <int n>
+    static __device__ __forceinline__ void run(const cplx (&tj)[Tri<D>::n][1 << O], QS<NB> (&out)[1 << O], int& Kmax) {
+        constexpr int ns = 1 << O;
+        if constexpr (n < NB) {
+            constexpr int lo = b2_block_lo(D, UMASK, n), hi = b2_partner(D, UMASK, lo);
+            cplx w[ns], u11[ns], u12[ns], u21[ns], u22[ns];
+#pragma unroll
+            for (int s = 0; s < ns; ++s) w[s] = tj[Tri<D>::idx(lo, hi)][s];
+            Kmax = max(Kmax, block2_exp<O, false>(nullptr, nullptr, w, u11, u12, u21, u22));
+#pragma unroll
+            for (int s = 0; s < ns; ++s) { out[s].a[n] = u11[s]; out[s].b[n] = u12[s]; }
+            run<n + 1>(tj, out, Kmax);
+        }
+    }
+};
+template <int D, unsigned UMASK, int O>
+__device__ __forceinline__ int q_step(const DevProblem& P, const StagedPlan& sp, const double* xk, const double* xadd, int k, int kind,
+                                      int v, int es, QS<b2_nblocks(D, UMASK)> (&out)[1 << O]) {
+    cplx tj[Tri<D>::n][1 << O];
+    b2_assemble<D, UMASK, O>(P, sp, xk, xadd, k, kind, v, es, tj);
+    int Kmax = 0;
+    QBlocks<D, UMASK, O>::template run<0>(tj, out, Kmax);
+    return Kmax;
+}
+
+// shared-memory slot of one pulse (in complex numbers)
+template <int D, unsigned UMASK> struct FQLayout {
+    static constexpr int NB = b2_nblocks(D, UMASK);
+    static constexpr int DD = D * D;
+    static constexpr int alg = 14 * DD + D + 1;             // fid_algebra scratch
+    static constexpr int tot = 4 * 4 * NB;                  // per warp of the pulse: inclusive totals (Q, V): 2 * 2 * NB, padded
+    static constexpr int fin = 4 * NB;                      // C_N, W_N
+    static constexpr int acc = 4 * RG_MAX_ADD;              // per warp x_add partial sums (as doubles: 4 warps x RG_MAX_ADD -> /2 cplx) + addT
+    static constexpr int slot = alg + tot + fin + acc + 1;
+};
+__host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int nent) {
+    const int DD = d * d;
+    const size_t slot = (size_t)(14 * DD + d + 1) + 16 * nb + 4 * nb + 4 * RG_MAX_ADD + 1;
+    return staged_plan_bytes(nterms, nent, d) + 4 * slot * sizeof(cplx);
+}
+
+#ifndef RG_FQ_CTAS
+#define RG_FQ_CTAS 3
+#endif
+
+// ERR = false: fidelity role.   Fout[b] = F (fmode 0) or 1 - F (fmode 1);  out[b*nx + ...] = scale0 * dF/dx  (x_add target part * scale0T)
+// ERR = true : role of error source e = blockIdx.y.  Fout[b*ne + e] = F_d2err[e];  out[(b*ne+e)*nx + ...] = dF_d2err[e]/dx
+template <int D, unsigned UMASK, bool ERR>
+__global__ void __launch_bounds__(128, ERR ? 2 : RG_FQ_CTAS)
+k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
+          int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int* __restrict__ status) {
+    constexpr int NB = b2_nblocks(D, UMASK);
+    constexpr int DD = D * D;
+    typedef FQLayout<D, UMASK> LY;
+    typedef QS<NB> Q;
+    extern __shared__ cplx smem[];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ppc = 4 / wpp;                                     // pulses per CTA
+    const int pslot = warp / wpp, wip = warp - pslot * wpp;      // pulse slot in the CTA, warp within the pulse
+    int b = blockIdx.x * ppc + pslot;
+    const bool live = b < B;
+    if (!live) b = B - 1;
+    const int t = wip * 32 + lane;                               // lane within the pulse = chunk index
+    const int es = ERR ? (int)blockIdx.y : 0;
+    const int ne = P.e, nv = P.nvar;
+    cplx* slot = smem + staged_plan_bytes(P.nterms, tp.nent, D) / sizeof(cplx) + (size_t)pslot * LY::slot;
+    cplx* alg = slot;
+    cplx* totQ = slot + LY::alg;                                 // [wpp][2 NB] Q totals, then [wpp][2 NB] V totals
+    cplx* totV = totQ + 8 * NB;
+    cplx* finC = slot + LY::alg + LY::tot;                       // C_N (2 NB), W_N (2 NB)
+    double* accS = reinterpret_cast<double*>(slot + LY::alg + LY::tot + LY::fin);      // [4][RG_MAX_ADD] partial sums, then addT [RG_MAX_ADD]
+    double* addT = accS + 4 * RG_MAX_ADD;
+    const double* xp = X + (size_t)b * P.nx;
+    double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
+    for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
+    const int k0 = min(P.N, t * L), k1 = min(P.N, k0 + L);
+    int Kmax = 0;
+
+    // ---- 1. forward sweep over the chunk
+    Q q, vq;
+    qs_identity(q); qs_zero(vq);
+    for (int k = k0; k < k1; ++k) {
+        for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        if constexpr (!ERR) {
+            Q u[1];
+            Kmax = max(Kmax, q_step<D, UMASK, 0>(P, sp, xk, xadd, k, B2_VALUE, 0, 0, u));
+            Q qn; qs_mul(qn, u[0], q); q = qn;
+        } else {
+            Q u[2];
+            Kmax = max(Kmax, q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, u));
+            Q vn; qs_mul(vn, u[0], vq); qs_mul<NB, true>(vn, u[1], q);          // V <- U V + D Q_old
+            Q qn; qs_mul(qn, u[0], q);
+            vq = vn; q = qn;
+        }
+    }
+    // ---- 2. inclusive ordered scan over the lanes of the pulse: (Q2,V2) o (Q1,V1) = (Q2 Q1, Q2 V1 + V2 Q1), later on the left
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const Q pq = qs_shfl_up(q, off);
+        Q pv;
+        if constexpr (ERR) pv = qs_shfl_up(vq, off);
+        if (lane >= off) {
+            if constexpr (ERR) { Q vn; qs_mul(vn, q, pv); qs_mul<NB, true>(vn, vq, pq); vq = vn; }
+            Q qn; qs_mul(qn, q, pq); q = qn;
+        }
+    }
+    if (wpp > 1) {
+        if (lane == 31) {
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                totQ[wip * 2 * NB + 2 * n] = q.a[n]; totQ[wip * 2 * NB + 2 * n + 1] = q.b[n];
+                if constexpr (ERR) { totV[wip * 2 * NB + 2 * n] = vq.a[n]; totV[wip * 2 * NB + 2 * n + 1] = vq.b[n]; }
+            }
+        }
+        __syncthreads();
+        for (int w2 = wip - 1; w2 >= 0; --w2) {                 // (q, vq) o tot[wip-1] o ... o tot[0]
+            Q pq, pv;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                pq.a[n] = totQ[w2 * 2 * NB + 2 * n]; pq.b[n] = totQ[w2 * 2 * NB + 2 * n + 1];
+                if constexpr (ERR) { pv.a[n] = totV[w2 * 2 * NB + 2 * n]; pv.b[n] = totV[w2 * 2 * NB + 2 * n + 1]; }
+            }
+            if constexpr (ERR) { Q vn; qs_mul(vn, q, pv); qs_mul<NB, true>(vn, vq, pq); vq = vn; }
+            Q qn; qs_mul(qn, q, pq); q = qn;
+        }
+    }
+    // the last lane of the pulse holds C_N (and W_N): publish them, and the dense matrix the algebra starts from
+    if (t == 32 * wpp - 1) {
+        cplx* mU = alg + 2 * DD;
+        for (int i = 0; i < DD; ++i) mU[i] = cmk(0.0, 0.0);
+        if constexpr (!ERR) {
+#pragma unroll
+            for (int l = 0; l < D; ++l)
+                if (b2_partner(D, UMASK, l) < 0) mU[l + D * l] = cmk(1.0, 0.0);      // untouched levels: U(l,l) = 1
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            finC[2 * n] = q.a[n]; finC[2 * n + 1] = q.b[n];
+            if constexpr (ERR) { finC[2 * NB + 2 * n] = vq.a[n]; finC[2 * NB + 2 * n + 1] = vq.b[n]; }
+            const cplx a = ERR ? cscale(vq.a[n], P.inv_eps) : q.a[n], bb = ERR ? cscale(vq.b[n], P.inv_eps) : q.b[n];
+            mU[lo + D * lo] = a; mU[lo + D * hi] = bb;
+            mU[hi + D * lo] = cmk(-bb.x, bb.y); mU[hi + D * hi] = cconj(a);
+        }
+    }
+    __syncthreads();
+    // ---- 3. fidelity algebra by D lanes of the pulse's first warp
+    if (wip == 0 && lane < D) {
+        constexpr unsigned amask = (1u << D) - 1u;
+        const double Fval = fid_algebra<D>(P, alg, xadd, ERR ? 1 + es : 0, lane, amask, addT, true);
+        if (live && lane == 0) {
+            if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
+            else Fout[(size_t)b * ne + es] = Fval;
+        }
+    }
+    __syncthreads();
+    if (!do_grad) { if (Kmax == 99) atomicOr(status, 2); return; }          // F / F_d2err only
+    // ---- 4. co-states at the end of this lane's chunk
+    Q g, h;
+    {
+        const cplx* mK = alg + 9 * DD;
+        Q kq, cn;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            const cplx m11 = mK[lo + D * lo], m12 = mK[lo + D * hi], m21 = mK[hi + D * lo], m22 = mK[hi + D * hi];
+            kq.a[n] = cmk(0.5 * (m11.x + m22.x), 0.5 * (m11.y - m22.y));            // (m11 + conj m22) / 2
+            kq.b[n] = cmk(0.5 * (m12.x - m21.x), 0.5 * (m12.y + m21.y));            // (m12 - conj m21) / 2
+            cn.a[n] = finC[2 * n]; cn.b[n] = finC[2 * n + 1];
+        }
+        Q bs; qs_muladj(bs, cn, q);                                                  // B_t = C_N P_t^dag
+        qs_mul(g, kq, bs);
+        if constexpr (ERR) {
+            Q wn;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) { wn.a[n] = finC[2 * NB + 2 * n]; wn.b[n] = finC[2 * NB + 2 * n + 1]; }
+            Q t1; qs_mul(t1, bs, vq);
+            Q t2; qs_sub(t2, wn, t1);
+            Q db; qs_muladj(db, t2, q);                                              // dB_t = (W_N - B_t V_t) P_t^dag
+            qs_mul(h, kq, db);
+        }
+    }
+    // ---- 5. backward sweep over the chunk
+    double acc[RG_MAX_ADD];
+#pragma unroll
+    for (int j = 0; j < RG_MAX_ADD; ++j) acc[j] = 0.0;
+    double* outb = ERR ? out + ((size_t)b * ne + es) * P.nx : out + (size_t)b * P.nx;
+    const double DD1 = P.Dtr * (P.Dtr + 1.0);
+    const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
+    for (int k = k1 - 1; k >= k0; --k) {
+        for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        if constexpr (!ERR) {
+            Q u, cp;
+            for (int v = 0; v < max(nv, 1); ++v) {
+                Q ud[2];
+                q_step<D, UMASK, 1>(P, sp, xk, xadd, k, nv ? B2_VAR : B2_VALUE, v, 0, ud);
+                if (v == 0) { u = ud[0]; qs_adjmul(cp, u, q); }                       // C_{k-1} = U_k^dag C_k
+                if (nv == 0) break;
+                Q tt; qs_mul(tt, ud[1], cp);                                         // dU C_{k-1}
+                const double s = qs_retrace(g, tt) * scale0;
+                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
+                else acc[P.var_index[v]] += s;
+            }
+            Q gn; qs_mul(gn, g, u);                                                  // G_{k-1} = G_k U_k
+            g = gn; q = cp;
+        } else {
+            Q ue[2];
+            q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, ue);
+            {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
+                Q cp; qs_adjmul(cp, ue[0], q); q = cp;
+                Q t1; qs_mul(t1, ue[1], q);
+                Q t2; qs_sub(t2, vq, t1);
+                qs_adjmul(vq, ue[0], t2);
+            }
+            for (int v = 0; v < nv; ++v) {
+                double s1, s2;
+                {
+                    Q ud[2];
+                    q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_VAR, v, 0, ud);
+                    Q tt; qs_mul(tt, ud[1], q);
+                    s1 = qs_retrace(h, tt);
+                    qs_mul(tt, ud[1], vq);
+                    s1 += qs_retrace(g, tt);
+                }
+                {
+                    Q u4[4];
+                    q_step<D, UMASK, 2>(P, sp, xk, xadd, k, B2_MIXED, v, es, u4);
+                    Q tt; qs_mul(tt, u4[3], q);
+                    s2 = qs_retrace(g, tt);
+                }
+                const double s = f1 * s1 + f2 * s2;
+                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
+                else acc[P.var_index[v]] += s;
+            }
+            {   // advance: H' <- H' U + G' D ;  G' <- G' U
+                Q hn; qs_mul(hn, h, ue[0]); qs_mul<NB, true>(hn, g, ue[1]);
+                Q gn; qs_mul(gn, g, ue[0]);
+                h = hn; g = gn;
+            }
+        }
+    }
+    // ---- x_add entries: fixed-order reduction over the pulse's lanes, plus the target-derivative part from the algebra
+    if (P.a > 0) {
+        for (int j = 0; j < P.a; ++j) {
+            double s = acc[j];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) accS[wip * RG_MAX_ADD + j] = s;
+        }
+        __syncthreads();
+        if (wip == 0 && lane < P.a && live) {
+            double s = 0.0;
+            for (int w2 = 0; w2 < wpp; ++w2) s += accS[w2 * RG_MAX_ADD + lane];
+            if (P.add_var[lane] < 0) s = 0.0;
+            outb[(size_t)P.p * P.N + lane] = s + (ERR ? 1.0 : scale0T) * addT[lane];
+        }
+    }
+    if (Kmax == 99) atomicOr(status, 2);
+}

@@ -78,6 +78,8 @@ struct rg_problem {
     int force_sequential_analysis = 0;   // RG_SEQ_ANALYSIS=1: time-sequential interaction-operator kernel
     int force_ws = 0;             // RG_WS=1: step-matrix workspace path even where the workspace-free block-2 path applies
     int b2_agg_ctas = 0, b2_grad_ctas = 0;   // resident CTAs/SM of the block-2 sweeps (occupancy query, cached)
+    int force_b2 = 0;             // RG_B2=1: three-kernel block-2 path even where the one-launch fused quaternion path applies
+    int fq_ctas[2] = {0, 0};      // resident CTAs/SM of k_fused_q (fidelity role, error role)
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
     double tri_density = 1.0;
@@ -111,9 +113,15 @@ int rg_b2_launch_agg(rg_problem* pr, const DevProblem& P, int B, int L, int nc, 
 int rg_b2_launch_grad(rg_problem* pr, const DevProblem& P, int B, int L, int nc, const double* dX, double* out0, double scale0);
 int rg_b2_launch_grad_err(rg_problem* pr, const DevProblem& P, int B, int L, int nc, const double* dX, double* out1);
 void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas);
+// one-launch fused quaternion path (rg_fusedq.cuh): block-2 patterns without diagonal terms
+int rg_fq_pattern(const rg_problem* pr);
+int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
+                 double scale0, double scale0T, int do_grad);
 static inline bool rg_use_b2(const rg_problem* pr) {
     return !pr->force_group && !pr->force_dense && !pr->force_group_sweeps && !pr->fused_agg && rg_b2_pattern(pr) != 0;
 }
+
+static inline bool rg_use_fq(const rg_problem* pr) { return rg_use_b2(pr) && !pr->force_b2 && rg_fq_pattern(pr) != 0; }
 
 // ---- per-dimension operations table (defined by RG_DEFINE_DIM in rg_dims_*.cu) --------------------------
 struct Plan;
@@ -270,6 +278,24 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         iFdx = pr->Fdx.as<double>();
     }
 
+    if (rg_use_fq(pr)) {
+        // one launch per role: forward sweep, scan, fidelity algebra, backward sweep (rg_fusedq.cuh)
+        const double DD1q = P.Dtr * (P.Dtr + 1.0);
+        const double sgn = (mode == 1 && ne == 0) ? -1.0 : 1.0;
+        const bool cost_fused = (mode == 1 && ne == 0);
+        int rc = rg_fq_launch(pr, P, B, dX, 0, cost_fused ? dF : iF, cost_fused ? 1 : 0, iFdx, sgn * P.inv_eps / DD1q, sgn, want_grad ? 1 : 0);
+        if (rc) return rc;
+        if (ne > 0) { rc = rg_fq_launch(pr, P, B, dX, 1, iF2, 0, iF2dx, 0.0, 1.0, want_grad ? 1 : 0); if (rc) return rc; }
+        if (mode == 1 && ne > 0) {
+            if (!want_grad) RG_FAIL(ctx, RG_ERR_INVALID, "cost without gradient is not exposed");
+            KTimer kt(ctx, RG_K_EPILOGUE);
+            const size_t n = (size_t)B * P.nx;
+            const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+            k_cost_grad<<<grid, 256, 0, st>>>(B, P.nx, ne, iF, iF2, iF2dx, d_coeff, dF, iFdx);
+        }
+        CU(ctx, cudaGetLastError());
+        return RG_OK;
+    }
     // ---- K1: step propagators + first-order differences (+ chunk aggregates)
     constexpr bool kThreadOK = (D <= 5);
     constexpr bool kSparseThread = (PID != PAT_FULL) && (Pat<D, CMS>::nnz <= 12);   // state fits one thread's registers

@@ -725,6 +725,100 @@ __device__ __forceinline__ cplx gtrace2(const cplx* A, const cplx* B, cplx* scra
     return greduce<D>(acc, scratch, l, amask);
 }
 
+// Fidelity algebra of one pulse, carried out by the D lanes of a group on matrices in shared memory (src/FidelityCalculations.jl
+// :54-65 for role 0, :79-97 for role 1+e, :35-40,72-74,102-109 for the target-derivative parts of the x_add gradient).
+//   in : base + 2*DD (mU) = U (role 0) or E_e = W_N/eps (role 1+e), column-major
+//   out: base + 9*DD (mK) = co-state seed K (role 0) or K' (role 1+e); returns F resp. F_d2err[e]; addT_dst[j] receives the
+//        target-derivative part of the x_add[j] gradient entry (written by lane 0 when `live`).
+// base needs (14*DD + D + 1) complex numbers.
+template <int D>
+__device__ __forceinline__ double fid_algebra(const DevProblem& P, cplx* base, const double* xadd, int role, int l, unsigned amask,
+                                              double* __restrict__ addT_dst, bool live) {
+    constexpr int DD = D * D;
+    cplx* mX = base; cplx* mW = base + DD; cplx* mU = base + 2 * DD; cplx* mU0 = base + 3 * DD; cplx* mM = base + 4 * DD;
+    cplx* T1 = base + 5 * DD; cplx* T2 = base + 6 * DD; cplx* T3 = base + 7 * DD; cplx* T4 = base + 8 * DD; cplx* mK = base + 9 * DD;
+    cplx* cPP = base + 10 * DD; cplx* cPPt = base + 11 * DD; cplx* cP = base + 12 * DD; cplx* mV = base + 13 * DD;
+    cplx* scratch = base + 14 * DD;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        cPP[i + D * l] = cmk(P.PP[i + D * l], 0.0);
+        cPPt[i + D * l] = cmk(P.PPt[i + D * l], 0.0);
+        cP[i + D * l] = cmk(P.Pm[i + D * l], 0.0);
+    }
+    // target U0(x_add)
+    {
+        EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
+        cplx* coef = mX;    // reuse as coefficient table (ntt <= D*D enforced on host)
+        __syncwarp(amask);
+        for (int t = l; t < P.ntt; t += D) {
+            cplx bb, dl;
+            term_coef(P.tterms[t], ec, RG_S_NONE, 0, 0.0, bb, dl);
+            coef[t] = bb;
+        }
+        __syncwarp(amask);
+        assemble_col<D>(P.tents, P.tcolptr, coef, mU0, l);
+    }
+    const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
+    gmm<D, OPC, OPN>(mM, mU0, mU, l, amask);              // M = U0^dag U   (or U0^dag E)
+    gmm<D, OPN, OPN>(T1, cPP, mM, l, amask);              // T1 = PP M
+    cplx tau = cmk(0.0, 0.0);
+    {
+        cplx d = T1[l + D * l];
+        tau = greduce<D>(d, scratch, l, amask);
+    }
+    gmm<D, OPN, OPC>(T2, cP, mM, l, amask);               // T2 = P M^dag
+    const cplx tr12 = gtrace2<D, OPN, OPN>(T1, T2, scratch, l, amask);
+    double Fval = (tr12.x + tau.x * tau.x + tau.y * tau.y) / DD1;
+    gmm<D, OPN, OPN>(T3, T2, cPP, l, amask);              // P M^dag PP
+    gmm<D, OPT, OPC>(T4, cP, mM, l, amask);               // P^T M^dag
+    gmm<D, OPN, OPN>(T3, T4, cPPt, l, amask, true);       // + P^T M^dag PP^T
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        cplx v = T3[i + D * l];
+        const double pp = P.PP[i + D * l];
+        v.x += 2.0 * tau.x * pp; v.y += -2.0 * tau.y * pp;   // + 2 conj(tau) PP
+        T3[i + D * l] = v;
+    }
+    gmm<D, OPN, OPC>(mK, T3, mU0, l, amask);              // K = R U0^dag
+    double scale_out = 1.0;
+    if (role > 0) {
+        // F_d2err = 2 [ Re tr(PP ME P ME^dag) - (1+D) Re tr(PP E^dag E) + |tau_e|^2 ] / (D(D+1))
+        gmm<D, OPC, OPN>(T4, mU, mU, l, amask);           // E^dag E
+        const cplx tee = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
+        Fval = 2.0 * (tr12.x - (1.0 + Dt) * tee.x + tau.x * tau.x + tau.y * tau.y) / DD1;
+        // K' = K - (1+D) (PP + PP^T) E^dag
+#pragma unroll
+        for (int i = 0; i < D; ++i) T4[i + D * l] = cmk(P.PP[i + D * l] + P.PPt[i + D * l], 0.0);
+        gmm<D, OPN, OPC>(mK, T4, mU, l, amask, true, -(1.0 + Dt));
+        scale_out = 2.0;
+    }
+    // ---- x_add: target-derivative parts (src/FidelityCalculations.jl:35-40,72-74,102,105,109)
+    for (int j = 0; j < P.a; ++j) {
+        EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
+        const double h = __dsub_rn(__dadd_rn(xadd[j], P.eps), xadd[j]);
+        cplx* coef = mX;
+        __syncwarp(amask);
+        for (int t = l; t < P.ntt; t += D) {
+            cplx bb, dl;
+            term_coef(P.tterms[t], ec, RG_S_ADD, j, h, bb, dl);
+            coef[t] = cscale(dl, P.inv_eps);
+        }
+        __syncwarp(amask);
+        assemble_col<D>(P.tents, P.tcolptr, coef, mV, l);
+        gmm<D, OPC, OPN>(mW, mV, mU, l, amask);           // S1 = V^dag U
+        const cplx t3 = gtrace2<D, OPN, OPN>(cPP, mW, scratch, l, amask);      // tr(PP V^dag U)
+        gmm<D, OPN, OPN>(T4, mW, T2, l, amask);           // S1 P M^dag
+        const cplx t1 = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
+        gmm<D, OPC, OPN>(mW, mU, mV, l, amask);           // U^dag V
+        gmm<D, OPN, OPN>(T4, cP, mW, l, amask);           // P U^dag V
+        const cplx t2 = gtrace2<D, OPN, OPN>(T1, T4, scratch, l, amask);        // tr(PP M P U^dag V)
+        const double val = scale_out * (t1.x + t2.x + 2.0 * (tau.x * t3.x + tau.y * t3.y)) / DD1;
+        if (live && l == 0) addT_dst[j] = val;
+    }
+    __syncwarp(amask);
+    return Fval;
+}
+
 // grid.y = role: 0 -> fidelity F and its co-state; 1+e -> sensitivity F_d2err[e] and its co-states
 template <int D>
 __global__ void __launch_bounds__(64)
@@ -876,84 +970,12 @@ k_scan(const DevProblem P, const double* __restrict__ X, int B, int nc,
 
     // ---- fidelity algebra
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        mU[i + D * l] = (role == 0) ? c[i] : cscale(w[i], P.inv_eps);   // E = W_N / eps
-        cPP[i + D * l] = cmk(P.PP[i + D * l], 0.0);
-        cPPt[i + D * l] = cmk(P.PPt[i + D * l], 0.0);
-        cP[i + D * l] = cmk(P.Pm[i + D * l], 0.0);
-    }
-    // target U0(x_add)
+    for (int i = 0; i < D; ++i) mU[i + D * l] = (role == 0) ? c[i] : cscale(w[i], P.inv_eps);   // E = W_N / eps
     {
-        EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
-        cplx* coef = mX;    // reuse as coefficient table (ntt <= D*D enforced on host)
-        __syncwarp(amask);
-        for (int t = l; t < P.ntt; t += D) {
-            cplx bb, dl;
-            term_coef(P.tterms[t], ec, RG_S_NONE, 0, 0.0, bb, dl);
-            coef[t] = bb;
+        const double Fval = fid_algebra<D>(P, base, xadd, role, l, amask, addT + ((size_t)b * (1 + ne) + role) * P.a, live);
+        if (live && l == 0) {
+            if (role == 0) Fout[b] = Fval; else F2out[(size_t)b * ne + es] = Fval;
         }
-        __syncwarp(amask);
-        assemble_col<D>(P.tents, P.tcolptr, coef, mU0, l);
-    }
-    const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
-    gmm<D, OPC, OPN>(mM, mU0, mU, l, amask);              // M = U0^dag U   (or U0^dag E)
-    gmm<D, OPN, OPN>(T1, cPP, mM, l, amask);              // T1 = PP M
-    cplx tau = cmk(0.0, 0.0);
-    {
-        cplx d = T1[l + D * l];
-        tau = greduce<D>(d, scratch, l, amask);
-    }
-    gmm<D, OPN, OPC>(T2, cP, mM, l, amask);               // T2 = P M^dag
-    const cplx tr12 = gtrace2<D, OPN, OPN>(T1, T2, scratch, l, amask);
-    double Fval = (tr12.x + tau.x * tau.x + tau.y * tau.y) / DD1;
-    gmm<D, OPN, OPN>(T3, T2, cPP, l, amask);              // P M^dag PP
-    gmm<D, OPT, OPC>(T4, cP, mM, l, amask);               // P^T M^dag
-    gmm<D, OPN, OPN>(T3, T4, cPPt, l, amask, true);       // + P^T M^dag PP^T
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        cplx v = T3[i + D * l];
-        const double pp = P.PP[i + D * l];
-        v.x += 2.0 * tau.x * pp; v.y += -2.0 * tau.y * pp;   // + 2 conj(tau) PP
-        T3[i + D * l] = v;
-    }
-    gmm<D, OPN, OPC>(mK, T3, mU0, l, amask);              // K = R U0^dag
-    double scale_out = 1.0;
-    if (role > 0) {
-        // F_d2err = 2 [ Re tr(PP ME P ME^dag) - (1+D) Re tr(PP E^dag E) + |tau_e|^2 ] / (D(D+1))
-        gmm<D, OPC, OPN>(T4, mU, mU, l, amask);           // E^dag E
-        const cplx tee = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
-        Fval = 2.0 * (tr12.x - (1.0 + Dt) * tee.x + tau.x * tau.x + tau.y * tau.y) / DD1;
-        // K' = K - (1+D) (PP + PP^T) E^dag
-#pragma unroll
-        for (int i = 0; i < D; ++i) T4[i + D * l] = cmk(P.PP[i + D * l] + P.PPt[i + D * l], 0.0);
-        gmm<D, OPN, OPC>(mK, T4, mU, l, amask, true, -(1.0 + Dt));
-        scale_out = 2.0;
-    }
-    if (live && l == 0) {
-        if (role == 0) Fout[b] = Fval; else F2out[(size_t)b * ne + es] = Fval;
-    }
-    // ---- x_add: target-derivative parts (src/FidelityCalculations.jl:35-40,72-74,102,105,109)
-    for (int j = 0; j < P.a; ++j) {
-        EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
-        const double h = __dsub_rn(__dadd_rn(xadd[j], P.eps), xadd[j]);
-        cplx* coef = mX;
-        __syncwarp(amask);
-        for (int t = l; t < P.ntt; t += D) {
-            cplx bb, dl;
-            term_coef(P.tterms[t], ec, RG_S_ADD, j, h, bb, dl);
-            coef[t] = cscale(dl, P.inv_eps);
-        }
-        __syncwarp(amask);
-        assemble_col<D>(P.tents, P.tcolptr, coef, mV, l);
-        gmm<D, OPC, OPN>(mW, mV, mU, l, amask);           // S1 = V^dag U
-        const cplx t3 = gtrace2<D, OPN, OPN>(cPP, mW, scratch, l, amask);      // tr(PP V^dag U)
-        gmm<D, OPN, OPN>(T4, mW, T2, l, amask);           // S1 P M^dag
-        const cplx t1 = gtrace2<D, OPN, OPN>(cPP, T4, scratch, l, amask);
-        gmm<D, OPC, OPN>(mW, mU, mV, l, amask);           // U^dag V
-        gmm<D, OPN, OPN>(T4, cP, mW, l, amask);           // P U^dag V
-        const cplx t2 = gtrace2<D, OPN, OPN>(T1, T4, scratch, l, amask);        // tr(PP M P U^dag V)
-        const double val = scale_out * (t1.x + t2.x + 2.0 * (tau.x * t3.x + tau.y * t3.y)) / DD1;
-        if (live && l == 0) addT[((size_t)b * (1 + ne) + role) * P.a + j] = val;
     }
     __syncwarp(amask);
 

@@ -508,12 +508,38 @@ def test_workspace_free_path_equals_workspace_path(gpu_ctx, monkeypatch, model, 
     d = 5 if model == "symmetric_blockaded" else 7
     X = 2 * np.pi * np.random.default_rng(17).random((N + 1, B))
     fp = cz_problem(N, 7.613 * N / 400, errors, model, delta=delta)
-    new = rg.calculate_fidelity_and_derivatives_batch(fp, X)
-    monkeypatch.setenv("RG_WS", "1")
+    new = rg.calculate_fidelity_and_derivatives_batch(fp, X)           # one-launch quaternion path where eligible, else block-2
+    monkeypatch.setenv("RG_B2", "1")                                   # three-kernel block-2 path
+    fp1 = cz_problem(N, 7.613 * N / 400, errors, model, delta=delta)
+    mid = rg.calculate_fidelity_and_derivatives_batch(fp1, X)
+    monkeypatch.setenv("RG_WS", "1")                                   # step-matrix workspace path
     fp2 = cz_problem(N, 7.613 * N / 400, errors, model, delta=delta)
     old = rg.calculate_fidelity_and_derivatives_batch(fp2, X)
+    for k, u, m, v in zip(NAMES, new, mid, old):
+        assert relmax(u, v) < 1e-11, (k, relmax(u, v))
+        assert relmax(m, v) < 1e-11, (k, relmax(m, v))
+    # cost/gradient epilogue of every path
+    coeff = [1e-4, 3e-4][:len(errors)]
+    c_old, g_old = rg.cost_and_gradient_batch(fp2, X, coeff)
+    monkeypatch.delenv("RG_WS"); monkeypatch.delenv("RG_B2")
+    fp3 = cz_problem(N, 7.613 * N / 400, errors, model, delta=delta)
+    c_new, g_new = rg.cost_and_gradient_batch(fp3, X, coeff)
+    assert np.abs(c_new - c_old).max() < 1e-12 and relmax(g_new, g_old) < 1e-11
+
+
+@pytest.mark.parametrize("N,B", [(1, 3), (7, 2), (31, 5), (64, 1), (500, 1), (1000, 150), (333, 1100)])
+def test_fused_quaternion_path_shapes(gpu_ctx, monkeypatch, N, B):
+    """One-launch fused path (rg_fusedq.cuh) over ragged shapes: fewer steps than lanes, one pulse (4 warps per pulse),
+    mid-size batches (2 warps per pulse), against the workspace path."""
+    X = 2 * np.pi * np.random.default_rng(N + B).random((N + 1, B))
+    fp = cz_problem(N, 7.613 * max(N, 20) / 1000, ("amp",))
+    new = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    new_nograd = rg.calculate_fidelity_and_derivatives_batch(fp, X, want_grad=False)
+    monkeypatch.setenv("RG_WS", "1")
+    old = rg.calculate_fidelity_and_derivatives_batch(cz_problem(N, 7.613 * max(N, 20) / 1000, ("amp",)), X)
     for k, u, v in zip(NAMES, new, old):
         assert relmax(u, v) < 1e-11, (k, relmax(u, v))
+    assert np.array_equal(new[0], new_nograd[0]) and np.array_equal(new[2], new_nograd[2])
 
 
 def test_block2_large_step_norm(gpu_ctx):
