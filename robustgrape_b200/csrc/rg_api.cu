@@ -149,7 +149,7 @@ static int flatten_terms(const rg_term* terms, int n, bool target, int d, std::v
         for (int f = 0; f < s.nfactors; ++f) {
             const rg_factor& ff = s.factors[f];
             if (ff.kind < RG_F_VAR || ff.kind > RG_F_TABLE) { why = "unknown factor kind"; return -1; }
-            o.f[f] = DevFactor{ff.kind, ff.space, ff.index, 0, ff.scale, ff.offset};
+            o.f[f] = DevFactor{ff.kind, ff.space, ff.index, -1, ff.scale, ff.offset};
         }
         for (int z = 0; z < s.nnz; ++z) {
             if (s.rows[z] < 0 || s.rows[z] >= d || s.cols[z] < 0 || s.cols[z] >= d) { why = "matrix entry out of range"; return -1; }
@@ -233,6 +233,29 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         }
     }
     P.nstore = 1 + P.nvar + P.e + P.nvar * P.e + (P.hermitian ? 0 : 1);     // + U^{-1} for non-Hermitian H
+    // trig slots: distinct arguments of the COS/SIN/EXPI factors, most frequent first (terms whose matrix holds no
+    // upper-triangle entry are never evaluated by the Hermitian fast paths and do not take a slot there)
+    P.ntrig = 0;
+    {
+        std::vector<int> has_upper(ht.size(), 0);
+        for (auto& en : he) if (en.row <= en.col) has_upper[en.term] = 1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t t = 0; t < ht.size(); ++t) {
+                if ((pass == 0) != (has_upper[t] != 0)) continue;
+                for (int f = 0; f < ht[t].nf; ++f) {
+                    DevFactor& ff = ht[t].f[f];
+                    if (ff.kind < RG_F_COS || ff.kind > RG_F_EXPI) continue;
+                    int slot = -1;
+                    for (int q = 0; q < P.ntrig; ++q)
+                        if (P.trig_space[q] == ff.space && P.trig_index[q] == ff.index && P.trig_scale[q] == ff.scale && P.trig_offset[q] == ff.offset) slot = q;
+                    if (slot < 0 && P.ntrig < RG_MAX_TRIG) {
+                        slot = P.ntrig++;
+                        P.trig_space[slot] = ff.space; P.trig_index[slot] = ff.index; P.trig_scale[slot] = ff.scale; P.trig_offset[slot] = ff.offset;
+                    }
+                    ff.slot = slot;
+                }
+            }
+    }
 
     P.nterms = (int)ht.size(); P.terms = upload(pr, ht);
     P.nent = (int)he.size(); P.ents = upload(pr, he); P.colptr = upload(pr, hc);
@@ -268,6 +291,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_SEQ_ANALYSIS")) pr->force_sequential_analysis = atoi(s);
     if (const char* s = getenv("RG_WS")) pr->force_ws = atoi(s);
     if (const char* s = getenv("RG_B2")) pr->force_b2 = atoi(s);
+    if (const char* s = getenv("RG_WPP")) pr->wpp_override = atoi(s);
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
     if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS) {
         const int npos = d * (d + 1) / 2;

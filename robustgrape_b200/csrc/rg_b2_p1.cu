@@ -1,0 +1,5 @@
+// three-kernel block-2 path, pattern 1 (see rg_block2_patterns.cuh)
+#define RG_B2_D 5
+#define RG_B2_ID 1
+#define RG_B2_MASK B2_M5_DRIVE
+#include "rg_b2_impl.inl"

@@ -29,18 +29,10 @@ __constant__ double c_sincq[14] = {1.0, -1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 
 
 // series degree K with remainder (K+1) z^{K+1}/(2K+2)! below 1e-17 (differences converge like the derivative series)
 __device__ __forceinline__ int b2_degree(double z) {
-    if (z <= 1.3e-5) return 2;
-    if (z <= 5.6e-4) return 3;
-    if (z <= 5.9e-3) return 4;
-    if (z <= 3.0e-2) return 5;
-    if (z <= 0.10) return 6;
-    if (z <= 0.26) return 7;
-    if (z <= 0.57) return 8;
-    if (z <= 1.05) return 9;
-    if (z <= 1.85) return 10;
-    if (z <= 2.95) return 11;
-    if (z <= 4.5) return 12;
-    return 99;
+    // branch-free: the number of thresholds below z
+    const int k = 2 + (z > 1.3e-5) + (z > 5.6e-4) + (z > 5.9e-3) + (z > 3.0e-2) + (z > 0.10) + (z > 0.26) + (z > 0.57) + (z > 1.05) +
+                  (z > 1.85) + (z > 2.95);
+    return (z > 4.5) ? 99 : k;
 }
 
 // ---- difference arithmetic ------------------------------------------------------------------------------------------
@@ -120,12 +112,27 @@ __device__ __forceinline__ int block2_exp(const double* a1, const double* a2, co
     C[0] = c_cosq[K]; S[0] = c_sincq[K];
 #pragma unroll
     for (int s = 1; s < n; ++s) { C[s] = 0.0; S[s] = 0.0; }
-    for (int j = K - 1; j >= 0; --j) {
-        jprod<O>(z, C, t1); jprod<O>(z, S, t2);
-#pragma unroll
-        for (int s = 0; s < n; ++s) { C[s] = t1[s]; S[s] = t2[s]; }
-        C[0] += c_cosq[j]; S[0] += c_sincq[j];
+    // Horner in difference arithmetic, v <- c_j + z v, entered at degree K and falling through to 0 (no loop overhead)
+#define RG_B2_SERIES_STEP(j)                                                              \
+    {                                                                                     \
+        jprod<O>(z, C, t1); jprod<O>(z, S, t2);                                           \
+        _Pragma("unroll") for (int s = 0; s < n; ++s) { C[s] = t1[s]; S[s] = t2[s]; }     \
+        C[0] += c_cosq[j]; S[0] += c_sincq[j];                                            \
     }
+    switch (K) {
+    case 12: RG_B2_SERIES_STEP(11)
+    case 11: RG_B2_SERIES_STEP(10)
+    case 10: RG_B2_SERIES_STEP(9)
+    case 9: RG_B2_SERIES_STEP(8)
+    case 8: RG_B2_SERIES_STEP(7)
+    case 7: RG_B2_SERIES_STEP(6)
+    case 6: RG_B2_SERIES_STEP(5)
+    case 5: RG_B2_SERIES_STEP(4)
+    case 4: RG_B2_SERIES_STEP(3)
+    case 3: RG_B2_SERIES_STEP(2)
+    default: RG_B2_SERIES_STEP(1) RG_B2_SERIES_STEP(0)
+    }
+#undef RG_B2_SERIES_STEP
     cplx o12[n];
     jprod<O>(S, w, o12);
     if constexpr (DIAG) {
@@ -167,7 +174,7 @@ enum { B2_VALUE = 0, B2_VAR = 1, B2_ERR = 2, B2_MIXED = 3 };
 //   O = 2, B2_MIXED  : a = difference of H0 in v at eps2, b = error Hamiltonian at eps2, ab = its difference in v (:76-79)
 template <int D, unsigned UMASK, int O>
 __device__ __forceinline__ void b2_assemble(const DevProblem& P, const StagedPlan& sp, const double* xk, const double* xadd, int k,
-                                            int kind, int v, int es, cplx (&tj)[Tri<D>::n][1 << O]) {
+                                            int kind, int v, int es, cplx (&tj)[Tri<D>::n][1 << O], const TrigSlots& tr) {
     constexpr int NP = Tri<D>::n;
     constexpr int n = 1 << O;
     int sp_ = RG_S_NONE, ix = 0;
@@ -180,7 +187,7 @@ __device__ __forceinline__ void b2_assemble(const DevProblem& P, const StagedPla
     }
     if (kind == B2_ERR) errv = P.eps;
     if (kind == B2_MIXED) errv = P.eps2;
-    EvalCtx ec{xk, xadd, errv, P.table, P.N, k};
+    EvalCtx ec{xk, xadd, errv, P.table, P.N, k, tr.n, tr.s0, tr.c0, tr.s1, tr.c1};
 #pragma unroll
     for (int pos = 0; pos < NP; ++pos)
 #pragma unroll
@@ -253,9 +260,9 @@ struct B2Blocks {
 
 template <int D, unsigned UMASK, int O>
 __device__ __forceinline__ int b2_step(const DevProblem& P, const StagedPlan& sp, const double* xk, const double* xadd, int k,
-                                       int kind, int v, int es, PMat<D, stored_from_tri(D, UMASK)> (&out)[1 << O]) {
+                                       int kind, int v, int es, PMat<D, stored_from_tri(D, UMASK)> (&out)[1 << O], const TrigSlots& tr) {
     cplx tj[Tri<D>::n][1 << O];
-    b2_assemble<D, UMASK, O>(P, sp, xk, xadd, k, kind, v, es, tj);
+    b2_assemble<D, UMASK, O>(P, sp, xk, xadd, k, kind, v, es, tj, tr);
     int Kmax = 0;
     B2Blocks<D, UMASK, O>::template run<0>(tj, out, Kmax);
     return Kmax;
@@ -293,8 +300,9 @@ k_agg_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, 
     if (ne == 0) {
         for (int k = k0; k < k1; ++k) {
             for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+            const TrigSlots tr = trig_eval(P, xk, xadd);
             M u[1];
-            Kmax = max(Kmax, b2_step<D, UMASK, 0>(P, sp, xk, xadd, k, B2_VALUE, 0, 0, u));
+            Kmax = max(Kmax, b2_step<D, UMASK, 0>(P, sp, xk, xadd, k, B2_VALUE, 0, 0, u, tr));
             M qn; pmat_mul<D, CMS, false, false>(qn, u[0], q);
             q = qn;
         }
@@ -304,8 +312,9 @@ k_agg_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, 
             M wl; wl.zero();
             for (int k = k0; k < k1; ++k) {
                 for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+                const TrigSlots tr = trig_eval(P, xk, xadd);
                 M u[2];
-                Kmax = max(Kmax, b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, e, u));
+                Kmax = max(Kmax, b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, e, u, tr));
                 M wn; pmat_mul<D, CMS, false, false>(wn, u[0], wl); pmat_mul<D, CMS, false, true>(wn, u[1], q);
                 M qn; pmat_mul<D, CMS, false, false>(qn, u[0], q);
                 wl = wn; q = qn;
@@ -349,11 +358,12 @@ k_grad_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     }
     for (int k = k1 - 1; k >= k0; --k) {
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        const TrigSlots tr = trig_eval(P, xk, xadd);
         M u;
         M cp;
         for (int v = 0; v < max(nv, 1); ++v) {
             M ud[2];
-            b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, nv ? B2_VAR : B2_VALUE, v, 0, ud);
+            b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, nv ? B2_VAR : B2_VALUE, v, 0, ud, tr);
             if (v == 0) { u = ud[0]; pmat_mul<D, CMS, true, false>(cp, u, c); }      // C_{k-1} = U_k^dag C_k
             if (nv == 0) break;
             M t; pmat_mul<D, CMS, false, false>(t, ud[1], cp);                        // dU C_{k-1}
@@ -405,8 +415,9 @@ k_grad_err_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict_
     }
     for (int k = k1 - 1; k >= k0; --k) {
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        const TrigSlots tr = trig_eval(P, xk, xadd);
         M ue[2];                               // U_k and D_k^e at err = eps
-        b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, ue);
+        b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, ue, tr);
         {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
             M cp; pmat_mul<D, CMS, true, false>(cp, ue[0], c);
             c = cp;
@@ -419,7 +430,7 @@ k_grad_err_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict_
             double s1, s2;
             {
                 M ud[2];
-                b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_VAR, v, 0, ud);
+                b2_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_VAR, v, 0, ud, tr);
                 M t; pmat_mul<D, CMS, false, false>(t, ud[1], c);
                 s1 = pmat_retrace<D, CMS>(h, t);
                 pmat_mul<D, CMS, false, false>(t, ud[1], w);
@@ -427,7 +438,7 @@ k_grad_err_b2(const DevProblem P, const TriPlanDev tp, const double* __restrict_
             }
             {
                 M u4[4];
-                b2_step<D, UMASK, 2>(P, sp, xk, xadd, k, B2_MIXED, v, es, u4);
+                b2_step<D, UMASK, 2>(P, sp, xk, xadd, k, B2_MIXED, v, es, u4, tr);
                 M t; pmat_mul<D, CMS, false, false>(t, u4[3], c);
                 s2 = pmat_retrace<D, CMS>(g, t);
             }

@@ -17,7 +17,8 @@
 
 typedef double2 cplx;
 
-struct DevFactor { int kind, space, index, pad; double scale, offset; };
+#define RG_MAX_TRIG 2     // distinct trigonometric arguments per step shared between factor evaluations (see TrigSlots)
+struct DevFactor { int kind, space, index, slot; double scale, offset; };   // slot: trig slot of this factor's argument, or -1
 struct DevTerm { int owner, nf; double cr, ci; DevFactor f[RG_MAX_FACTORS]; };
 struct DevEntry { int row, col, term, pad; double vr, vi; };
 
@@ -37,6 +38,9 @@ struct DevProblem {
     int add_var[RG_MAX_ADD];   // index into vars for each additional parameter, or -1
     int ntab; const double* table;
     int hermitian;
+    int ntrig;           // trig slots: distinct arguments u = scale * v + offset of the COS/SIN/EXPI factors of H0 and error terms
+    int trig_space[RG_MAX_TRIG], trig_index[RG_MAX_TRIG];
+    double trig_scale[RG_MAX_TRIG], trig_offset[RG_MAX_TRIG];
     int nx;              // p*N + a
     int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
     int wsm;             // complex elements stored per step matrix (d*d, or the closure pattern's nnz)
@@ -98,7 +102,14 @@ struct EvalCtx {
     const double* xadd;    // additional parameters (a)
     double errv;           // error amplitude seen by ERR factors
     const double* table; int N; int k;   // per-step table, 0-based step
+    int ntrig;             // > 0: sin/cos of the trig slots were evaluated once for this step (TrigSlots)
+    double ts0, tc0, ts1, tc1;
 };
+// sin/cos of every distinct trigonometric argument of the step, evaluated once and shared by all coefficient evaluations
+// of that step (the e^{-i phi} of the drive appears in H0 and in every amplitude-type error term, and each of the
+// value / variable / error / mixed evaluations of a step would otherwise call sincos again).
+struct TrigSlots { int n; double s0, c0, s1, c1; };
+__device__ __forceinline__ TrigSlots trig_eval(const DevProblem& P, const double* xk, const double* xadd);
 
 __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int pspace, int pindex, double h,
                                    cplx& val, cplx& del) {
@@ -116,7 +127,8 @@ __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int psp
     const double hu = dep ? f.scale * h : 0.0;
     if (f.kind == RG_F_VAR) { val = cmk(u, 0.0); del = cmk(hu, 0.0); return; }
     double s, co;
-    sincos(u, &s, &co);
+    if (c.ntrig > 0 && f.slot >= 0) { s = f.slot == 0 ? c.ts0 : c.ts1; co = f.slot == 0 ? c.tc0 : c.tc1; }
+    else sincos(u, &s, &co);
     // e^{ihu} - 1 = -2 sin^2(hu/2) + i sin(hu)
     double er = 0.0, ei = 0.0;
     if (dep) {
@@ -140,6 +152,21 @@ __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int psp
         val = cmk(s, 0.0);
         del = cmk(co * ei + s * er, 0.0);          // Im(e^{iu}(e^{ih}-1))
     }
+}
+
+__device__ __forceinline__ TrigSlots trig_eval(const DevProblem& P, const double* xk, const double* xadd) {
+    TrigSlots t{P.ntrig, 0.0, 1.0, 0.0, 1.0};
+    if (P.ntrig > 0) {
+        const double v = (P.trig_space[0] == RG_S_MAIN) ? xk[P.trig_index[0]] : xadd[P.trig_index[0]];
+        const bool plain = (P.trig_scale[0] == 1.0 && P.trig_offset[0] == 0.0);
+        sincos(plain ? v : fma(P.trig_scale[0], v, P.trig_offset[0]), &t.s0, &t.c0);
+    }
+    if (P.ntrig > 1) {
+        const double v = (P.trig_space[1] == RG_S_MAIN) ? xk[P.trig_index[1]] : xadd[P.trig_index[1]];
+        const bool plain = (P.trig_scale[1] == 1.0 && P.trig_offset[1] == 0.0);
+        sincos(plain ? v : fma(P.trig_scale[1], v, P.trig_offset[1]), &t.s1, &t.c1);
+    }
+    return t;
 }
 
 // Term coefficient and its finite difference in variable (pspace,pindex) with step h:

@@ -1,0 +1,5 @@
+// one-launch fused quaternion path, pattern 1 (see rg_block2_patterns.cuh)
+#define RG_B2_D 5
+#define RG_B2_ID 1
+#define RG_B2_MASK B2_M5_DRIVE
+#include "rg_fq_impl.inl"

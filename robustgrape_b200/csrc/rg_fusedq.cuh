@@ -142,9 +142,9 @@ struct QBlocks {
 };
 template <int D, unsigned UMASK, int O>
 __device__ __forceinline__ int q_step(const DevProblem& P, const StagedPlan& sp, const double* xk, const double* xadd, int k, int kind,
-                                      int v, int es, QS<b2_nblocks(D, UMASK)> (&out)[1 << O]) {
+                                      int v, int es, QS<b2_nblocks(D, UMASK)> (&out)[1 << O], const TrigSlots& tr) {
     cplx tj[Tri<D>::n][1 << O];
-    b2_assemble<D, UMASK, O>(P, sp, xk, xadd, k, kind, v, es, tj);
+    b2_assemble<D, UMASK, O>(P, sp, xk, xadd, k, kind, v, es, tj, tr);
     int Kmax = 0;
     QBlocks<D, UMASK, O>::template run<0>(tj, out, Kmax);
     return Kmax;
@@ -209,13 +209,14 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     qs_identity(q); qs_zero(vq);
     for (int k = k0; k < k1; ++k) {
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {
             Q u[1];
-            Kmax = max(Kmax, q_step<D, UMASK, 0>(P, sp, xk, xadd, k, B2_VALUE, 0, 0, u));
+            Kmax = max(Kmax, q_step<D, UMASK, 0>(P, sp, xk, xadd, k, B2_VALUE, 0, 0, u, tr));
             Q qn; qs_mul(qn, u[0], q); q = qn;
         } else {
             Q u[2];
-            Kmax = max(Kmax, q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, u));
+            Kmax = max(Kmax, q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, u, tr));
             Q vn; qs_mul(vn, u[0], vq); qs_mul<NB, true>(vn, u[1], q);          // V <- U V + D Q_old
             Q qn; qs_mul(qn, u[0], q);
             vq = vn; q = qn;
@@ -317,11 +318,12 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
     for (int k = k1 - 1; k >= k0; --k) {
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+        const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {
             Q u, cp;
             for (int v = 0; v < max(nv, 1); ++v) {
                 Q ud[2];
-                q_step<D, UMASK, 1>(P, sp, xk, xadd, k, nv ? B2_VAR : B2_VALUE, v, 0, ud);
+                q_step<D, UMASK, 1>(P, sp, xk, xadd, k, nv ? B2_VAR : B2_VALUE, v, 0, ud, tr);
                 if (v == 0) { u = ud[0]; qs_adjmul(cp, u, q); }                       // C_{k-1} = U_k^dag C_k
                 if (nv == 0) break;
                 Q tt; qs_mul(tt, ud[1], cp);                                         // dU C_{k-1}
@@ -333,7 +335,7 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             g = gn; q = cp;
         } else {
             Q ue[2];
-            q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, ue);
+            q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_ERR, 0, es, ue, tr);
             {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
                 Q cp; qs_adjmul(cp, ue[0], q); q = cp;
                 Q t1; qs_mul(t1, ue[1], q);
@@ -344,7 +346,7 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
                 double s1, s2;
                 {
                     Q ud[2];
-                    q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_VAR, v, 0, ud);
+                    q_step<D, UMASK, 1>(P, sp, xk, xadd, k, B2_VAR, v, 0, ud, tr);
                     Q tt; qs_mul(tt, ud[1], q);
                     s1 = qs_retrace(h, tt);
                     qs_mul(tt, ud[1], vq);
@@ -352,7 +354,7 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
                 }
                 {
                     Q u4[4];
-                    q_step<D, UMASK, 2>(P, sp, xk, xadd, k, B2_MIXED, v, es, u4);
+                    q_step<D, UMASK, 2>(P, sp, xk, xadd, k, B2_MIXED, v, es, u4, tr);
                     Q tt; qs_mul(tt, u4[3], q);
                     s2 = qs_retrace(g, tt);
                 }

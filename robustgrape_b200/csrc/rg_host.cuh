@@ -26,8 +26,8 @@ struct rg_ctx {
     size_t ws_limit = (size_t)64 << 30;
     // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
-    int host_slabs = 4;                               // RG_HOST_SLABS (upper bound on the number of slabs)
-    int host_slab_min = 2048;                         // RG_HOST_SLAB_MIN (smallest slab, pulses)
+    int host_slabs = 8;                               // RG_HOST_SLABS (upper bound on the number of slabs)
+    int host_slab_min = 1024;                         // RG_HOST_SLAB_MIN (smallest slab, pulses)
     cudaStream_t s_peer[2] = {nullptr, nullptr};      // side streams of rg_gather_to_peers (created on first use)
     cudaEvent_t ev_src = nullptr, ev_peer_join = nullptr, ev_gather[2] = {nullptr, nullptr};
     bool gather_pending[2] = {false, false};
@@ -79,6 +79,7 @@ struct rg_problem {
     int force_ws = 0;             // RG_WS=1: step-matrix workspace path even where the workspace-free block-2 path applies
     int b2_agg_ctas = 0, b2_grad_ctas = 0;   // resident CTAs/SM of the block-2 sweeps (occupancy query, cached)
     int force_b2 = 0;             // RG_B2=1: three-kernel block-2 path even where the one-launch fused quaternion path applies
+    int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
     int fq_ctas[2] = {0, 0};      // resident CTAs/SM of k_fused_q (fidelity role, error role)
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
