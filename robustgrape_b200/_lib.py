@@ -13,7 +13,8 @@ import numpy as np
 
 from . import descriptors as D
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "librobustgrape_b200.so"
+# RG_LIB_PATH: load a differently-built copy of the library (kernel A/B experiments); default = the in-tree build
+LIB_PATH = Path(os.environ.get("RG_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "librobustgrape_b200.so")
 
 RG_OK, RG_ERR_INVALID, RG_ERR_CUDA, RG_ERR_UNSUPPORTED, RG_ERR_NORM, RG_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 MAX_FACTORS = 4

@@ -112,13 +112,17 @@ __device__ __forceinline__ int block2_exp(const double* a1, const double* a2, co
     C[0] = c_cosq[K]; S[0] = c_sincq[K];
 #pragma unroll
     for (int s = 1; s < n; ++s) { C[s] = 0.0; S[s] = 0.0; }
-    // Horner in difference arithmetic, v <- c_j + z v, entered at degree K and falling through to 0 (no loop overhead)
+    // Horner in difference arithmetic, v <- c_j + z v
+#ifndef RG_B2_SERIES_SWITCH
+#define RG_B2_SERIES_SWITCH 1      // 1: fall-through switch instead of a loop (measured on B200, C4: 0.647 vs 0.683 ms)
+#endif
 #define RG_B2_SERIES_STEP(j)                                                              \
     {                                                                                     \
         jprod<O>(z, C, t1); jprod<O>(z, S, t2);                                           \
         _Pragma("unroll") for (int s = 0; s < n; ++s) { C[s] = t1[s]; S[s] = t2[s]; }     \
         C[0] += c_cosq[j]; S[0] += c_sincq[j];                                            \
     }
+#if RG_B2_SERIES_SWITCH
     switch (K) {
     case 12: RG_B2_SERIES_STEP(11)
     case 11: RG_B2_SERIES_STEP(10)
@@ -132,6 +136,9 @@ __device__ __forceinline__ int block2_exp(const double* a1, const double* a2, co
     case 3: RG_B2_SERIES_STEP(2)
     default: RG_B2_SERIES_STEP(1) RG_B2_SERIES_STEP(0)
     }
+#else
+    for (int j = K - 1; j >= 0; --j) RG_B2_SERIES_STEP(j)
+#endif
 #undef RG_B2_SERIES_STEP
     cplx o12[n];
     jprod<O>(S, w, o12);

@@ -155,7 +155,11 @@ __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int psp
 }
 
 __device__ __forceinline__ TrigSlots trig_eval(const DevProblem& P, const double* xk, const double* xadd) {
-    TrigSlots t{P.ntrig, 0.0, 1.0, 0.0, 1.0};
+#ifndef RG_TRIG_SLOTS
+#define RG_TRIG_SLOTS 0      // measured on B200 (C4): sharing sincos through trig slots is slower (0.68 vs 0.57 ms; longer live ranges), so off
+#endif
+    TrigSlots t{RG_TRIG_SLOTS ? P.ntrig : 0, 0.0, 1.0, 0.0, 1.0};
+    if (!RG_TRIG_SLOTS) return t;
     if (P.ntrig > 0) {
         const double v = (P.trig_space[0] == RG_S_MAIN) ? xk[P.trig_index[0]] : xadd[P.trig_index[0]];
         const bool plain = (P.trig_scale[0] == 1.0 && P.trig_offset[0] == 0.0);
