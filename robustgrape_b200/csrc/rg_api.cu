@@ -7,7 +7,12 @@
 #define RG_DECL_DIM(D) extern const DimOps rg_ops_d##D;
 RG_DECL_DIM(2) RG_DECL_DIM(3) RG_DECL_DIM(4) RG_DECL_DIM(5) RG_DECL_DIM(6) RG_DECL_DIM(7) RG_DECL_DIM(8) RG_DECL_DIM(9)
 RG_DECL_DIM(10)
+extern const DimOps rg_ops_big16, rg_ops_big32, rg_ops_big48, rg_ops_big64;      // dense DMMA path, 11 <= ndim <= 64 (rg_big.cuh)
 const DimOps* rg_dim_ops(int d) {
+    if (d > 10 && d <= 16) return &rg_ops_big16;
+    if (d > 16 && d <= 32) return &rg_ops_big32;
+    if (d > 32 && d <= 48) return &rg_ops_big48;
+    if (d > 48 && d <= 64) return &rg_ops_big64;
     switch (d) {
     case 2: return &rg_ops_d2; case 3: return &rg_ops_d3; case 4: return &rg_ops_d4; case 5: return &rg_ops_d5;
     case 6: return &rg_ops_d6; case 7: return &rg_ops_d7; case 8: return &rg_ops_d8; case 9: return &rg_ops_d9;
@@ -171,7 +176,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
     const int d = desc->ndim;
-    if (!supported_dim(d)) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "ndim=%d not supported by the small-d path (2..10, 12, 16)", d);
+    if (!supported_dim(d)) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "ndim=%d not supported (2 <= ndim <= 64)", d);
     if (desc->ntimes < 1) RG_FAIL(ctx, RG_ERR_INVALID, "ntimes must be >= 1");
     if (desc->nparam < 0 || desc->nparam > RG_MAX_MAIN) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "nparam=%d (max %d)", desc->nparam, RG_MAX_MAIN);
     if (desc->nb_additional_param < 0 || desc->nb_additional_param > RG_MAX_ADD)
@@ -198,6 +203,22 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (flatten_terms(desc->terms, desc->nterms, false, d, ht, he, hc, why)) return fail(RG_ERR_INVALID, why);
     if (flatten_terms(desc->target_terms, desc->ntarget_terms, true, d, tt, te, tc, why)) return fail(RG_ERR_INVALID, why);
     if ((int)tt.size() > d * d) return fail(RG_ERR_UNSUPPORTED, "too many target terms");
+    if (d > 10) {
+        // dense path: every term as a dense planar matrix (re plane, im plane), padded to a multiple of 16
+        const int DPb = ((d + 15) / 16) * 16;
+        const size_t plane = (size_t)DPb * DPb;
+        auto dense = [&](const std::vector<DevTerm>& terms, const std::vector<DevEntry>& ents, DevBuf& buf) -> int {
+            std::vector<double> h(std::max<size_t>(1, terms.size()) * 2 * plane, 0.0);
+            for (auto& en : ents) {
+                h[(size_t)en.term * 2 * plane + (size_t)en.row * DPb + en.col] += en.vr;
+                h[(size_t)en.term * 2 * plane + plane + (size_t)en.row * DPb + en.col] += en.vi;
+            }
+            if (buf.ensure(h.size() * 8)) return -1;
+            return cudaMemcpy(buf.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+        };
+        if (dense(ht, he, pr->big_termM) || dense(tt, te, pr->big_tgtM)) return fail(RG_ERR_NOMEM, "dense term upload failed");
+        pr->big_dp = DPb;
+    }
     for (auto& t : ht)
         if (t.owner < RG_OWNER_H0 || t.owner >= P.e) return fail(RG_ERR_INVALID, "term owner out of range");
     // range checks on variable references
@@ -357,6 +378,7 @@ extern "C" void rg_problem_destroy(rg_problem* pr) {
     if (!pr) return;
     cudaSetDevice(pr->ctx->device);
     for (void* p : pr->owned) cudaFree(p);
+    pr->big_termM.release(); pr->big_tgtM.release();
     DevBuf* bufs[] = {&pr->ws, &pr->Qb, &pr->Wlb, &pr->Cb, &pr->Wb, &pr->Gb, &pr->G1b, &pr->H1b, &pr->F, &pr->F2,
                       &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq, &pr->dM};
     for (DevBuf* b : bufs) b->release();

@@ -79,6 +79,9 @@ struct rg_problem {
     int force_ws = 0;             // RG_WS=1: step-matrix workspace path even where the workspace-free block-2 path applies
     int b2_agg_ctas = 0, b2_grad_ctas = 0;   // resident CTAs/SM of the block-2 sweeps (occupancy query, cached)
     int force_b2 = 0;             // RG_B2=1: three-kernel block-2 path even where the one-launch fused quaternion path applies
+    // dense path (rg_big.cuh, ndim > 10): dense planar term matrices, padded dimension, occupancy of k_big_steps
+    DevBuf big_termM, big_tgtM;
+    int big_dp = 0, big_ctas = 0;
     int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
     int fq_ctas[2] = {0, 0};      // resident CTAs/SM of k_fused_q (fidelity role, error role)
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
@@ -164,6 +167,17 @@ static inline Plan make_plan(rg_problem* pr, int B) {
         L = std::max(1, std::min(L, P.N));
         pl.L = L;
         pl.nc = (P.N + L - 1) / L;
+        return pl;
+    }
+    if (pr->big_dp) {
+        // dense path: per-step workspace of planar matrices; chunks sized so that (pulse, chunk) items fill the GPU a few times
+        const size_t per_pulse = (size_t)P.N * (size_t)pr->big_dp * pr->big_dp * (4 + 4 * P.e + 2 * P.nvar + 2 * P.nvar * P.e) * 8;
+        pl.slab = (int)std::min<size_t>(std::max<size_t>(1, pr->ctx->ws_limit / std::max<size_t>(per_pulse, 1)), (size_t)B);
+        const long long want = 2LL * pr->ctx->sm_count;
+        int L = (int)std::max<long long>(1, std::min<long long>(32, (long long)P.N * pl.slab / want));
+        if (pr->chunk_override > 0) L = pr->chunk_override;
+        L = std::max(1, std::min(L, P.N));
+        pl.L = L; pl.nc = (P.N + L - 1) / L;
         return pl;
     }
     const size_t per_pulse = (size_t)P.N * P.nstore * P.d * P.d * sizeof(cplx);

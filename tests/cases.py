@@ -92,6 +92,11 @@ def golden_cases():
     # BASELINE.json configs[1] at full size: examples/ar_cz.jl (N = 200, t0 = 14.32, amplitude error)
     fp = cz_problem(200, 14.32, ("amp",))
     cases["cz5_C2_e1_N200"] = (fp, random_pulse(fp, 1, 21))
+    # dense random-Hermitian control problems on the DMMA path (BASELINE config 5 in miniature); the last needs squarings
+    fp = dense_random_problem(16, 4, nparam=2, nerr=2, seed=16)
+    cases["dense16_p2_e2_N4"] = (fp, np.random.default_rng(116).uniform(-1, 1, 8))
+    fp = dense_random_problem(32, 3, nparam=2, nerr=1, seed=32, t0=1.2)
+    cases["dense32_p2_e1_N3_squared"] = (fp, np.random.default_rng(132).uniform(-1, 1, 6))
     # detuned 5- and 7-level models (diagonal terms inside the 2 x 2 blocks), two error sources
     fp = cz_problem(31, 7.613 * 31 / 100, ("freq", "amp"), delta=0.37, eps=0.02)
     cases["cz5_detuned_e2_N31"] = (fp, random_pulse(fp, 1, 22))

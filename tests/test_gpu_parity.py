@@ -320,13 +320,14 @@ def test_unitary_and_derivatives_materialised(gpu_ctx, case):
         assert np.abs(got[2][:, :, j] - r).max() <= tol_ex * max(np.abs(r).max(), 1e-30) + 1e-300
 
 
-@pytest.mark.parametrize("d", [3, 6, 10])
-def test_dense_random_hamiltonians(gpu_ctx, d):
+@pytest.mark.parametrize("d,N", [(3, 9), (6, 9), (10, 9), (11, 9), (12, 9), (16, 9), (24, 7), (32, 5), (48, 4), (64, 4)])
+def test_dense_random_hamiltonians(gpu_ctx, d, N):
     """Dense random-Hermitian control problems (BASELINE config 5 in miniature): p = 2 controls, one error source, no
-    additional parameters, identity-block projector, constant target.  d = 10, 12, 16 run the general (group) kernels."""
+    additional parameters, identity-block projector, constant target.  d <= 10 runs the general group kernels, d >= 11 the
+    DMMA path (rg_big.cuh: jets of planar matrices, Paterson-Stockmeyer Taylor + squarings)."""
     from cases import dense_random_problem
-    fp = dense_random_problem(d, 9, nparam=2, nerr=1, seed=d)
-    X = np.stack([np.random.default_rng(s).uniform(-1, 1, 18) for s in range(3)], axis=1)
+    fp = dense_random_problem(d, N, nparam=2, nerr=1, seed=d)
+    X = np.stack([np.random.default_rng(s).uniform(-1, 1, 2 * N) for s in range(3)], axis=1)
     F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
     for b in range(3):
         a = ro.calculate_fidelity_and_derivatives(fp, X[:, b])
@@ -553,3 +554,24 @@ def test_block2_large_step_norm(gpu_ctx):
         ex = eo.calculate_fidelity_and_derivatives(fp, x)
         for k, g, e in zip(NAMES, got, ex):
             assert relmax(g, e) < tol, (N, k, relmax(g, e))
+
+
+def test_dense_path_config5_shape(gpu_ctx):
+    """BASELINE.json configs[4] in miniature on the DMMA path: d = 64, p = 8 controls, e = 4 error sources (57 jet slots),
+    norm ||dt H||_1 ~ 3 (squarings), N = 3: all four outputs against the literal restatement at its noise floor, and the
+    cost/gradient epilogue."""
+    from cases import dense_random_problem
+    fp = dense_random_problem(64, 3, nparam=8, nerr=4, seed=5, t0=3 * 0.12)
+    X = np.stack([np.random.default_rng(60 + s).uniform(-1, 1, 24) for s in range(2)], axis=1)
+    F, Fdx, F2, F2dx = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    for b in range(2):
+        a = ro.calculate_fidelity_and_derivatives(fp, X[:, b])
+        assert abs(F[b] - a[0]) < 1e-12
+        assert relmax(Fdx[:, b], a[1]) < 2e-5
+        assert relmax(F2[:, b], a[2]) < 2e-5
+        assert relmax(F2dx[:, :, b], a[3]) < 2e-4
+    coeff = [1e-4, 2e-4, 3e-4, 4e-4]
+    c, g = rg.cost_and_gradient_batch(fp, X, coeff)
+    c2 = 1 - F + sum(coeff[e] * F2[e] ** 2 for e in range(4))
+    g2 = -Fdx + sum(2 * coeff[e] * F2[e][None, :] * F2dx[:, e, :] for e in range(4))
+    assert np.abs(c - c2).max() < 1e-13 and np.abs(g - g2).max() < 1e-12
