@@ -175,6 +175,142 @@ def workload_config(args, world=1, scaling="weak", gather="peer"):
     }
 
 
+def canonical_flops_dense(d, N, p, a, e, nrm1):
+    """SURVEY.md section 8(d) with the Pade degree / squarings Higham's thresholds pick for ||dt H||_1 = nrm1."""
+    pis = ((0.015, 2), (0.25, 3), (0.95, 4), (2.1, 5), (5.4, 6))
+    s, pi_m = 0, None
+    for th, pm in pis:
+        if nrm1 <= th:
+            pi_m = pm
+            break
+    if pi_m is None:
+        s = int(np.ceil(np.log2(nrm1 / 5.4)))
+        pi_m = 6
+    n_exp_needed = 1 + p + a + e * (2 + p + a) + ((p + a) if e > 0 else 0)
+    return 8.0 * d ** 3 * N * (n_exp_needed * (pi_m + 4.0 / 3.0 + s) + 4 + 8 * e)
+
+
+def make_dense_problem(d, N, p, e, target_norm, seed=64):
+    """BASELINE.json configs[4]: H(k) = H_0 + sum_j x_j(k) H_j, Herr_e = err * E_e, GUE draws scaled to unit spectral norm
+    (default_rng(64)), x ~ U(-1, 1), projector = identity on the first 16 levels, Haar-random target on that block (default_rng(65)),
+    dt chosen so that max_k ||dt H(k)||_1 = target_norm.  Returns (problem, x, realised 1-norm range)."""
+    import robustgrape_b200 as rg
+    from robustgrape_b200.descriptors import (Factor, Term, TermHamiltonian, TermErrorHamiltonian, ConstantTarget, S_MAIN, OWNER_H0)
+    rng = np.random.default_rng(seed)
+
+    def gue():
+        g = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        h = (g + g.conj().T) / 2
+        return h / np.linalg.norm(h, 2)
+
+    def ent(M):
+        return tuple((r, c, M[r, c]) for r in range(d) for c in range(d))
+
+    Hs = [gue() for _ in range(1 + p)]
+    Es = [gue() for _ in range(e)]
+    x = np.random.default_rng(seed + 2).uniform(-1, 1, p * N)
+    xs = x.reshape(N, p)
+    sample = xs[:: max(1, N // 64)]
+    n1 = np.array([np.abs(Hs[0] + sum(xx[j] * Hs[1 + j] for j in range(p))).sum(axis=0).max() for xx in sample])
+    dt = target_norm / n1.max()
+    terms = [Term(1.0, (), ent(Hs[0]), OWNER_H0)] + [Term(1.0, (Factor.var(S_MAIN, j),), ent(Hs[1 + j]), OWNER_H0) for j in range(p)]
+    srcs = [rg.ErrorSource(TermErrorHamiltonian(d, [Term(1.0, (Factor.err(),), ent(Es[i]), i)])) for i in range(e)]
+    nb = min(d, 16)
+    proj = np.zeros((d, d)); proj[:nb, :nb] = np.eye(nb)
+    r65 = np.random.default_rng(seed + 1)
+    q, _ = np.linalg.qr(r65.normal(size=(nb, nb)) + 1j * r65.normal(size=(nb, nb)))
+    U0 = np.zeros((d, d), dtype=complex); U0[:nb, :nb] = q
+    up = rg.UnitaryRobustGRAPEProblem(t0=dt * N, ntimes=N, ndim=d, H0=TermHamiltonian(d, terms), nb_additional_param=0, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, proj, ConstantTarget(U0)), x, (float(n1.min() * dt), float(n1.max() * dt))
+
+
+def run_dense(args):
+    """--workload C5 | d16: one pulse of the synthetic dense problem (d = 64 or 16, N = 1e4, p = 8, e = 4) on the DMMA path."""
+    import torch
+    from robustgrape_b200._lib import Context, Problem
+    d = 64 if args.workload == "C5" else 16
+    N, p, e = args.dense_ntimes, 8, 4
+    fp, x, nrm = make_dense_problem(d, N, p, e, args.dense_norm)
+    ctx = Context(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    prob = Problem(fp, ctx)
+    nx = p * N
+    B = args.dense_batch
+    X = np.stack([x] + [np.random.default_rng(700 + b).uniform(-1, 1, nx) for b in range(1, B)], axis=0)
+    dX = torch.from_numpy(X).cuda()
+    out = torch.empty(B * (nx + 1), dtype=torch.float64, device="cuda")
+    coeff = [1e-4] * e
+    peak_dfma, peak_dmma = ctx.measure_fp64_peak(0.3)
+
+    def step():
+        prob.cost_and_grad_batch_dev(B, nx, dX.data_ptr(), coeff, out[:B].data_ptr(), out[B:].data_ptr())
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    l0 = ctx.launch_count
+    sampler = ClockSampler(0)
+    sampler.__enter__()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.__exit__(None, None, None)
+    launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    ctx.set_timing(True); ctx.get_timing(reset=True)
+    step()
+    timing = ctx.get_timing(reset=True)
+    ctx.set_timing(False)
+    kernel_ms = {k: v[0] / v[1] for k, v in timing.items() if v[1]}
+    # e2e through the host-buffer C-ABI call
+    hX = np.asfortranarray(X.T)
+    t = time.perf_counter()
+    cost_h, grad_h = prob.cost_and_grad_batch(hX, coeff)
+    e2e_s = time.perf_counter() - t
+    cost_d = out[:B].cpu().numpy()
+    assert np.allclose(cost_h, cost_d, rtol=0, atol=1e-12)
+    # executed products: 5 + s jet products of 1 + 4 nf + 4 nv ne matrix products each (the last one skips the 2 nf eps2 slots),
+    # sweeps: aggregate 1 + 2e, gradient 3 + 9e per step
+    DP = ((d + 15) // 16) * 16
+    nf, nve = p + e, p * e
+    s_sq = max(0, int(np.ceil(np.log2((nrm[1] * 1.001) / 0.31))))
+    per_jet = 1 + 2 * (2 * nf) + 4 * nve
+    steps_prods = (5 + s_sq) * per_jet - 2 * nf - 3 * nve      # last stage skips the eps2 slots; the error terms do not depend on the
+    prods_step = steps_prods + (1 + 2 * e) + (3 + 9 * e)         # controls, so B's mixed slots vanish: B*B and B2*B skip 2 + 1 products per pair
+    executed = prods_step * 8.0 * DP ** 3 * N
+    canonical = canonical_flops_dense(d, N, p, 0, e, nrm[1])
+    dom = max(kernel_ms, key=kernel_ms.get)
+    exec_dom = steps_prods * 8.0 * DP ** 3 * N * B
+    ach_exec = exec_dom / (kernel_ms[dom] * 1e-3) / 1e12 if dom == "k_steps" else None
+    ach_canon = min(executed, canonical) * B / (ms * 1e-3) / 1e12
+    line = {
+        "metric": "GRAPE cost+grad evals/sec (dense synthetic, DMMA path)", "value": B / (ms * 1e-3), "unit": "evals/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: d={d}, N={N}, p={p}, a=0, e={e}, {B} pulse(s); GUE H_j and E_e scaled to unit spectral norm, "
+                               f"x ~ U(-1,1), ||dt H||_1 in [{nrm[0]:.2f}, {nrm[1]:.2f}] ({s_sq} squarings of a degree-12 Taylor polynomial), "
+                               "projector = first 16 levels, Haar target (BASELINE.json configs[4] / SURVEY 8d)",
+                   "l2": "per-step workspace (3.2 MB/step at d=64) and jet scratch far exceed L2"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": B / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(B * nx * 8), "d2h_bytes_per_step": int(B * (nx + 1) * 8)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "kernel": "k_big_steps (jets of planar matrices, DMMA m8n8k4 products)",
+                     "achieved": ach_exec, "peak": peak_dmma, "unit": "TFLOP/s", "frac": (ach_exec / peak_dmma) if ach_exec else None,
+                     "traffic": None, "peak_source": "DMMA m8n8k4 microbenchmark run by this process (DFMA loop: %.1f TFLOP/s)" % peak_dfma,
+                     "flops_per_eval": {"canonical_survey_8d": canonical, "executed": executed, "executed_products_per_step": prods_step},
+                     "whole_step_canonical": {"achieved_tflops": ach_canon, "frac_of_dmma_peak": ach_canon / peak_dmma,
+                                              "rule": "min(executed, canonical) / whole-step time (SURVEY 8d)"},
+                     "note": "exact finite differences cost 2 products per value product for first differences and 4 for mixed second "
+                             "differences, so executed flops exceed the canonical (independent Pade exponentials) count; both are reported",
+                     "kernel_ms": kernel_ms},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +323,11 @@ def main():
     ap.add_argument("--cpu-pulses-per-thread", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16"],
+                    help="C4 (default): multi-start CZ batch, the headline; C5 / d16: dense synthetic problem on the DMMA path (1 GPU)")
+    ap.add_argument("--dense-ntimes", type=int, default=10000)
+    ap.add_argument("--dense-norm", type=float, default=2.4, help="max_k ||dt H(k)||_1 of the dense workload (SURVEY 8d: 2.1 ... 5.4)")
+    ap.add_argument("--dense-batch", type=int, default=1)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --batch pulses per GPU (default), strong = --batch pulses in total")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
@@ -196,6 +337,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload != "C4":
+        run_dense(args)
         return
 
     import torch

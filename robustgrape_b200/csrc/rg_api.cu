@@ -254,6 +254,11 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         }
     }
     P.nstore = 1 + P.nvar + P.e + P.nvar * P.e + (P.hermitian ? 0 : 1);     // + U^{-1} for non-Hermitian H
+    P.mixed_zero = 1;
+    for (auto& t : ht)
+        if (t.owner >= 0)
+            for (int f = 0; f < t.nf; ++f)
+                if (t.f[f].kind <= RG_F_EXPI) P.mixed_zero = 0;
     // trig slots: distinct arguments of the COS/SIN/EXPI factors, most frequent first (terms whose matrix holds no
     // upper-triangle entry are never evaluated by the Hermitian fast paths and do not take a slot there)
     P.ntrig = 0;

@@ -48,32 +48,47 @@ struct BigGemm {
     }
     // acc += op(X) * op(sum_i Y_i).  Left needs rows [i][k]: N -> (re, im), H -> (reT, -imT).  Right needs rows [n][k]:
     // N -> (reT, imT), H -> (re, -im).  All threads of the CTA must call; sm holds SMEM_DOUBLES doubles.
-    __device__ __forceinline__ void mac(double* sm, const BMat& X, int opX, const BMat* Y, int nY, int opY) {
+    template <int NY>
+    __device__ __forceinline__ void mac(double* sm, const BMat& X, int opX, const BMat* Y, int opY) {
         const double* xr = opX == BOP_N ? X.re : X.reT;
         const double* xi = opX == BOP_N ? X.im : X.imT;
+        const double* yrp[NY]; const double* yip[NY];
+#pragma unroll
+        for (int q = 0; q < NY; ++q) { yrp[q] = opY == BOP_N ? Y[q].reT : Y[q].re; yip[q] = opY == BOP_N ? Y[q].imT : Y[q].im; }
         const double sx = opX == BOP_N ? 1.0 : -1.0, sy = opY == BOP_N ? 1.0 : -1.0;
         double* sLr = sm; double* sLi = sm + DP * RG_BIG_LDK; double* sRr = sm + 2 * DP * RG_BIG_LDK; double* sRi = sm + 3 * DP * RG_BIG_LDK;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int g = lane >> 2, t = lane & 3;
         const int row0 = (warp / (DP / 16)) * (DP / 2), col0 = (warp % (DP / 16)) * 16;
+        constexpr int ITER = DP * (RG_BIG_KC / 2) / NT;          // = 2: staging items per thread and chunk
+        static_assert(ITER * NT == DP * (RG_BIG_KC / 2), "staging must divide evenly over the CTA");
         for (int k0 = 0; k0 < DP; k0 += RG_BIG_KC) {
-            __syncthreads();                       // previous chunk consumed
-            // stage: DP rows x 16 doubles per plane, two doubles per thread and iteration
-            for (int idx = threadIdx.x; idx < DP * (RG_BIG_KC / 2); idx += NT) {
+            // all global loads of the chunk are issued before the first use (independent 16-byte loads in flight)
+            double2 a[ITER], b[ITER], u[ITER][NY], v[ITER][NY];
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const int idx = threadIdx.x + it * NT;
                 const int r = idx / (RG_BIG_KC / 2), c = (idx % (RG_BIG_KC / 2)) * 2;
                 const size_t go = (size_t)r * DP + k0 + c;
-                const double2 a = *reinterpret_cast<const double2*>(xr + go);
-                double2 b = *reinterpret_cast<const double2*>(xi + go);
-                b.x *= sx; b.y *= sx;
-                *reinterpret_cast<double2*>(sLr + r * RG_BIG_LDK + c) = a;
-                *reinterpret_cast<double2*>(sLi + r * RG_BIG_LDK + c) = b;
-                double2 yr = make_double2(0.0, 0.0), yi = make_double2(0.0, 0.0);
-                for (int q = 0; q < nY; ++q) {
-                    const double* pr = opY == BOP_N ? Y[q].reT : Y[q].re;
-                    const double* pi = opY == BOP_N ? Y[q].imT : Y[q].im;
-                    const double2 u = *reinterpret_cast<const double2*>(pr + go), v = *reinterpret_cast<const double2*>(pi + go);
-                    yr.x += u.x; yr.y += u.y; yi.x += v.x; yi.y += v.y;
+                a[it] = *reinterpret_cast<const double2*>(xr + go);
+                b[it] = *reinterpret_cast<const double2*>(xi + go);
+#pragma unroll
+                for (int q = 0; q < NY; ++q) {
+                    u[it][q] = *reinterpret_cast<const double2*>(yrp[q] + go);
+                    v[it][q] = *reinterpret_cast<const double2*>(yip[q] + go);
                 }
+            }
+            __syncthreads();                       // previous chunk consumed
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const int idx = threadIdx.x + it * NT;
+                const int r = idx / (RG_BIG_KC / 2), c = (idx % (RG_BIG_KC / 2)) * 2;
+                b[it].x *= sx; b[it].y *= sx;
+                *reinterpret_cast<double2*>(sLr + r * RG_BIG_LDK + c) = a[it];
+                *reinterpret_cast<double2*>(sLi + r * RG_BIG_LDK + c) = b[it];
+                double2 yr = u[it][0], yi = v[it][0];
+#pragma unroll
+                for (int q = 1; q < NY; ++q) { yr.x += u[it][q].x; yr.y += u[it][q].y; yi.x += v[it][q].x; yi.y += v[it][q].y; }
                 yi.x *= sy; yi.y *= sy;
                 *reinterpret_cast<double2*>(sRr + r * RG_BIG_LDK + c) = yr;
                 *reinterpret_cast<double2*>(sRi + r * RG_BIG_LDK + c) = yi;
@@ -83,30 +98,37 @@ struct BigGemm {
             for (int kk = 0; kk < RG_BIG_KC; kk += 4) {
                 double ar[WM], ai[WM], nai[WM], br[WN], bi[WN];
 #pragma unroll
-                for (int a = 0; a < WM; ++a) {
-                    ar[a] = sLr[(row0 + a * 8 + g) * RG_BIG_LDK + kk + t];
-                    ai[a] = sLi[(row0 + a * 8 + g) * RG_BIG_LDK + kk + t];
-                    nai[a] = -ai[a];
+                for (int a2 = 0; a2 < WM; ++a2) {
+                    ar[a2] = sLr[(row0 + a2 * 8 + g) * RG_BIG_LDK + kk + t];
+                    ai[a2] = sLi[(row0 + a2 * 8 + g) * RG_BIG_LDK + kk + t];
+                    nai[a2] = -ai[a2];
                 }
 #pragma unroll
-                for (int b = 0; b < WN; ++b) {
-                    br[b] = sRr[(col0 + b * 8 + g) * RG_BIG_LDK + kk + t];
-                    bi[b] = sRi[(col0 + b * 8 + g) * RG_BIG_LDK + kk + t];
+                for (int b2 = 0; b2 < WN; ++b2) {
+                    br[b2] = sRr[(col0 + b2 * 8 + g) * RG_BIG_LDK + kk + t];
+                    bi[b2] = sRi[(col0 + b2 * 8 + g) * RG_BIG_LDK + kk + t];
                 }
 #pragma unroll
-                for (int a = 0; a < WM; ++a)
+                for (int a2 = 0; a2 < WM; ++a2)
 #pragma unroll
-                    for (int b = 0; b < WN; ++b) {
-                        dmma884(cr[a][b][0], cr[a][b][1], ar[a], br[b]);
-                        dmma884(cr[a][b][0], cr[a][b][1], nai[a], bi[b]);
-                        dmma884(ci[a][b][0], ci[a][b][1], ar[a], bi[b]);
-                        dmma884(ci[a][b][0], ci[a][b][1], ai[a], br[b]);
+                    for (int b2 = 0; b2 < WN; ++b2) {
+                        dmma884(cr[a2][b2][0], cr[a2][b2][1], ar[a2], br[b2]);
+                        dmma884(cr[a2][b2][0], cr[a2][b2][1], nai[a2], bi[b2]);
+                        dmma884(ci[a2][b2][0], ci[a2][b2][1], ar[a2], bi[b2]);
+                        dmma884(ci[a2][b2][0], ci[a2][b2][1], ai[a2], br[b2]);
                     }
             }
         }
     }
-    // Z = alpha * acc [+ beta * Add] [+ gamma * I on the first d diagonal entries]; writes the transposed planes when present.
-    __device__ __forceinline__ void store(const BMat& Z, double alpha, const BMat* Add, double beta, double gamma, int d) {
+    // run-time source count (sweeps): dispatch to the unrolled versions
+    __device__ __forceinline__ void mac(double* sm, const BMat& X, int opX, const BMat* Y, int nY, int opY) {
+        if (nY == 1) mac<1>(sm, X, opX, Y, opY);
+        else if (nY == 2) mac<2>(sm, X, opX, Y, opY);
+        else mac<4>(sm, X, opX, Y, opY);
+    }
+    // Z = alpha * acc + sum_q beta[q] * Add[q] (canonical planes, q < nadd <= 3) [+ gamma * I on the first d diagonal entries];
+    // writes the transposed planes when present.
+    __device__ __forceinline__ void store(const BMat& Z, double alpha, const BMat* Add, const double* beta, int nadd, double gamma, int d) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int g = lane >> 2, t = lane & 3;
         const int row0 = (warp / (DP / 16)) * (DP / 2), col0 = (warp % (DP / 16)) * 16;
@@ -117,10 +139,10 @@ struct BigGemm {
                 const int r = row0 + a * 8 + g, c = col0 + b * 8 + 2 * t;
                 double2 vr = make_double2(alpha * cr[a][b][0], alpha * cr[a][b][1]);
                 double2 vi = make_double2(alpha * ci[a][b][0], alpha * ci[a][b][1]);
-                if (Add) {
-                    const double2 pr = *reinterpret_cast<const double2*>(Add->re + (size_t)r * DP + c);
-                    const double2 pi = *reinterpret_cast<const double2*>(Add->im + (size_t)r * DP + c);
-                    vr.x = fma(beta, pr.x, vr.x); vr.y = fma(beta, pr.y, vr.y); vi.x = fma(beta, pi.x, vi.x); vi.y = fma(beta, pi.y, vi.y);
+                for (int q = 0; q < nadd; ++q) {
+                    const double2 pr = *reinterpret_cast<const double2*>(Add[q].re + (size_t)r * DP + c);
+                    const double2 pi = *reinterpret_cast<const double2*>(Add[q].im + (size_t)r * DP + c);
+                    vr.x = fma(beta[q], pr.x, vr.x); vr.y = fma(beta[q], pr.y, vr.y); vi.x = fma(beta[q], pi.x, vi.x); vi.y = fma(beta[q], pi.y, vi.y);
                 }
                 if (gamma != 0.0 && r < d) { if (c == r) vr.x += gamma; if (c + 1 == r) vr.y += gamma; }
                 *reinterpret_cast<double2*>(Z.re + (size_t)r * DP + c) = vr;
@@ -130,6 +152,9 @@ struct BigGemm {
                     Z.imT[(size_t)c * DP + r] = vi.x; Z.imT[(size_t)(c + 1) * DP + r] = vi.y;
                 }
             }
+    }
+    __device__ __forceinline__ void store(const BMat& Z, double alpha, const BMat* Add, double beta, double gamma, int d) {
+        store(Z, alpha, Add, &beta, Add ? 1 : 0, gamma, d);
     }
 };
 
@@ -215,11 +240,13 @@ __device__ __forceinline__ BMat big_ws_d2U(double* ws, int nv, int ne, int v, in
     return bmat_at(ws + (size_t)DP * DP * (4 + 4 * ne + 2 * nv + 2 * (e * nv + v)), (size_t)DP * DP, false);
 }
 
-// Z = [Add +] X (x) Y, the exact jet product.  `final_ws` != nullptr: last stage -- only the slots the sweeps need are formed
-// and they go to the step workspace instead of scratch.  gamma: identity added to the value slot.
+// Z = X (x) Y [+ a1 A1 + a2 A2 + a3 A3 + gamma I], the exact jet product with a fused linear-combination epilogue (slot-wise;
+// the identity only in the value slot).  `final_ws` != nullptr: last stage -- only the slots the sweeps need are formed and they
+// go to the step workspace instead of scratch.  xz / yz: the mixed slots of X / Y are identically zero (B itself, when no error
+// term depends on a control), so the products with them are skipped.
 template <int DP>
-__device__ __noinline__ void jet_product(double* sm, double* Z, double* X, double* Y, double* Add, double gamma, int nv, int ne, int d,
-                                            double* final_ws) {
+__device__ __noinline__ void jet_product(double* sm, double* Z, double* X, double* Y, double* A1, double* A2, double* A3, double a1,
+                                         double a2, double a3, double gamma, int nv, int ne, int d, double* final_ws, bool xz, bool yz) {
     BigGemm<DP> G;
     const int nf = nv + ne, nslots = big_nslots(nv, ne);
     for (int s = 0; s < nslots; ++s) {
@@ -235,44 +262,51 @@ __device__ __noinline__ void jet_product(double* sm, double* Z, double* X, doubl
         const BMat X0 = jet_slot<DP>(X, 0), Y0 = jet_slot<DP>(Y, 0);
         G.zero();
         if (s == 0) {
-            G.mac(sm, X0, BOP_N, &Y0, 1, BOP_N);
+            G.template mac<1>(sm, X0, BOP_N, &Y0, BOP_N);
         } else if (s <= 2 * nf) {
             const BMat Xf = jet_slot<DP>(X, s), Yf = jet_slot<DP>(Y, s);
             const BMat ys[2] = {Y0, Yf};
-            G.mac(sm, Xf, BOP_N, ys, 2, BOP_N);
-            G.mac(sm, X0, BOP_N, &Yf, 1, BOP_N);
+            G.template mac<2>(sm, Xf, BOP_N, ys, BOP_N);
+            G.template mac<1>(sm, X0, BOP_N, &Yf, BOP_N);
         } else {
             const int q = s - 1 - 2 * nf, v = q % nv, e = q / nv;
             const int sa = 1 + nf + v, sb = 1 + nf + nv + e;
             const BMat Xa = jet_slot<DP>(X, sa), Xb = jet_slot<DP>(X, sb), Xab = jet_slot<DP>(X, s);
             const BMat Ya = jet_slot<DP>(Y, sa), Yb = jet_slot<DP>(Y, sb), Yab = jet_slot<DP>(Y, s);
-            const BMat y4[4] = {Y0, Ya, Yb, Yab};
-            G.mac(sm, Xab, BOP_N, y4, 4, BOP_N);
-            const BMat y2a[2] = {Yb, Yab};
-            G.mac(sm, Xa, BOP_N, y2a, 2, BOP_N);
-            const BMat y2b[2] = {Ya, Yab};
-            G.mac(sm, Xb, BOP_N, y2b, 2, BOP_N);
-            G.mac(sm, X0, BOP_N, &Yab, 1, BOP_N);
+            if (!xz) { const BMat y4[4] = {Y0, Ya, Yb, Yab}; G.template mac<4>(sm, Xab, BOP_N, y4, BOP_N); }
+            if (yz) {
+                G.template mac<1>(sm, Xa, BOP_N, &Yb, BOP_N);
+                G.template mac<1>(sm, Xb, BOP_N, &Ya, BOP_N);
+            } else {
+                const BMat y2a[2] = {Yb, Yab};
+                G.template mac<2>(sm, Xa, BOP_N, y2a, BOP_N);
+                const BMat y2b[2] = {Ya, Yab};
+                G.template mac<2>(sm, Xb, BOP_N, y2b, BOP_N);
+                G.template mac<1>(sm, X0, BOP_N, &Yab, BOP_N);
+            }
         }
-        BMat add;
-        if (Add) add = jet_slot<DP>(Add, s);
-        G.store(dst, 1.0, Add ? &add : nullptr, 1.0, s == 0 ? gamma : 0.0, d);
+        BMat adds[3]; double bc[3]; int na = 0;
+        if (A1) { adds[na] = jet_slot<DP>(A1, s); bc[na++] = a1; }
+        if (A2) { adds[na] = jet_slot<DP>(A2, s); bc[na++] = a2; }
+        if (A3) { adds[na] = jet_slot<DP>(A3, s); bc[na++] = a3; }
+        G.store(dst, 1.0, adds, bc, na, s == 0 ? gamma : 0.0, d);
     }
     __syncthreads();
 }
 
-// Z = c0 I + c1 J1 + c2 J2 + c3 J3 + c4 J4 slot-wise (identity only in the value slot); J4 may be null.
+// Transposed planes of Z = c0 I + c1 J1 + c2 J2 + c3 J3 + c4 J4, slot-wise (identity only in the value slot).  Z is only ever
+// used as a right operand (which reads reT / imT), so its canonical planes are not formed.
 template <int DP>
-__device__ __noinline__ void jet_lincomb(double* Z, double c0, double c1, double* J1, double c2, double* J2, double c3, double* J3,
-                                            double c4, double* J4, int nslots, int d, int nt) {
-    const size_t per = (size_t)4 * DP * DP;
-    for (size_t idx = threadIdx.x; idx < per * nslots; idx += nt) {
-        double v = c1 * J1[idx] + c2 * J2[idx] + c3 * J3[idx];
-        if (J4) v = fma(c4, J4[idx], v);
-        if (idx < per) {                                     // value slot: + c0 on the diagonal of the real planes
-            const size_t pl = idx / ((size_t)DP * DP), e = idx % ((size_t)DP * DP);
-            const int r = (int)(e / DP), c = (int)(e % DP);
-            if ((pl == 0 || pl == 2) && r == c && r < d) v += c0;
+__device__ __noinline__ void jet_lincomb_T(double* Z, double c0, double c1, double* J1, double c2, double* J2, double c3, double* J3,
+                                           double c4, double* J4, int nslots, int d, int nt) {
+    const size_t plane = (size_t)DP * DP, half = 2 * plane;
+    for (size_t it = threadIdx.x; it < half * nslots; it += nt) {
+        const size_t s = it / half, e2 = it % half;
+        const size_t idx = s * 4 * plane + 2 * plane + e2;            // planes 2, 3 of slot s
+        double v = c1 * J1[idx] + c2 * J2[idx] + c3 * J3[idx] + c4 * J4[idx];
+        if (s == 0 && e2 < plane) {
+            const int r = (int)(e2 / DP), c = (int)(e2 % DP);
+            if (r == c && r < d) v += c0;
         }
         Z[idx] = v;
     }
@@ -293,7 +327,7 @@ k_big_steps(const DevProblem P, const BigData Bd, const double* __restrict__ X, 
     const size_t plane = (size_t)DP * DP, jet = (size_t)nslots * 4 * plane;
     double* scr = Bd.scratch + (size_t)blockIdx.x * Bd.scratch_per_cta;
     double* JB = scr; double* J2 = scr + jet; double* J3 = scr + 2 * jet; double* J4 = scr + 3 * jet; double* JR = scr + 4 * jet;
-    double* JT = scr + 5 * jet; double* JP = scr + 6 * jet;
+    double* JT = scr + 5 * jet;
     const long long tasks = (long long)B * P.N;
     for (long long task = blockIdx.x; task < tasks; task += gridDim.x) {
         const int b = (int)(task / P.N), k = (int)(task % P.N);
@@ -388,18 +422,19 @@ k_big_steps(const DevProblem P, const BigData Bd, const double* __restrict__ X, 
         __syncthreads();
         // ---- degree-12 Taylor polynomial, Paterson-Stockmeyer with B^2, B^3, B^4 (5 jet products), then s squarings
         double* wsk = ws + (size_t)task * big_ws_step_doubles(DP, nv, ne);
-        jet_product<DP>(sm, J2, JB, JB, nullptr, 0.0, nv, ne, d, nullptr);
-        jet_product<DP>(sm, J3, J2, JB, nullptr, 0.0, nv, ne, d, nullptr);
-        jet_product<DP>(sm, J4, J2, J2, nullptr, 0.0, nv, ne, d, nullptr);
-        // R2 = c8 I + c9 B + c10 B2 + c11 B3 + c12 B4 ;  P1 = c4 I + c5 B + c6 B2 + c7 B3
-        jet_lincomb<DP>(JR, 1.0 / 40320, 1.0 / 362880, JB, 1.0 / 3628800, J2, 1.0 / 39916800, J3, 1.0 / 479001600, J4, nslots, d, NT);
-        jet_lincomb<DP>(JP, 1.0 / 24, 1.0 / 120, JB, 1.0 / 720, J2, 1.0 / 5040, J3, 0.0, nullptr, nslots, d, NT);
-        jet_product<DP>(sm, JT, J4, JR, JP, 0.0, nv, ne, d, nullptr);                      // R1 = P1 + B4 R2
-        jet_lincomb<DP>(JP, 1.0, 1.0, JB, 0.5, J2, 1.0 / 6, J3, 0.0, nullptr, nslots, d, NT);   // P0
-        jet_product<DP>(sm, JR, J4, JT, JP, 0.0, nv, ne, d, sq == 0 ? wsk : nullptr);     // T = P0 + B4 R1
+        const bool bz = P.mixed_zero != 0;
+        jet_product<DP>(sm, J2, JB, JB, nullptr, nullptr, nullptr, 0, 0, 0, 0.0, nv, ne, d, nullptr, bz, bz);
+        jet_product<DP>(sm, J3, J2, JB, nullptr, nullptr, nullptr, 0, 0, 0, 0.0, nv, ne, d, nullptr, false, bz);
+        jet_product<DP>(sm, J4, J2, J2, nullptr, nullptr, nullptr, 0, 0, 0, 0.0, nv, ne, d, nullptr, false, false);
+        // R2 = c8 I + c9 B + c10 B2 + c11 B3 + c12 B4 (right operand only)
+        jet_lincomb_T<DP>(JR, 1.0 / 40320, 1.0 / 362880, JB, 1.0 / 3628800, J2, 1.0 / 39916800, J3, 1.0 / 479001600, J4, nslots, d, NT);
+        // R1 = P1 + B4 R2,  P1 = c4 I + c5 B + c6 B2 + c7 B3 fused into the epilogue
+        jet_product<DP>(sm, JT, J4, JR, JB, J2, J3, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 24, nv, ne, d, nullptr, false, false);
+        // T = P0 + B4 R1,  P0 = I + B + B2/2 + B3/6
+        jet_product<DP>(sm, JR, J4, JT, JB, J2, J3, 1.0, 0.5, 1.0 / 6, 1.0, nv, ne, d, sq == 0 ? wsk : nullptr, false, false);
         double* cur = JR; double* nxt = JT;
         for (int q2 = 0; q2 < sq; ++q2) {
-            jet_product<DP>(sm, nxt, cur, cur, nullptr, 0.0, nv, ne, d, q2 == sq - 1 ? wsk : nullptr);
+            jet_product<DP>(sm, nxt, cur, cur, nullptr, nullptr, nullptr, 0, 0, 0, 0.0, nv, ne, d, q2 == sq - 1 ? wsk : nullptr, false, false);
             double* tmp = cur; cur = nxt; nxt = tmp;
         }
     }

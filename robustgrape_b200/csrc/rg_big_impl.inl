@@ -23,13 +23,13 @@ int big_run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mo
     rc = set_smem(ctx, k_big_scan<DP>, smem_sweep); if (rc) return rc;
     if (!pr->big_ctas) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->big_ctas, k_big_steps<DP>, GM::NT, smem_steps);
-        pr->big_ctas = std::max(1, std::min(pr->big_ctas, 4));
+        pr->big_ctas = std::max(1, std::min(pr->big_ctas, DP <= 16 ? 16 : (DP <= 32 ? 8 : 4)));
     }
     const long long tasks = (long long)B * P.N;
     const int grid_steps = (int)std::min<long long>(tasks, (long long)ctx->sm_count * pr->big_ctas);
     const int grid_sweep = (int)std::min<long long>((long long)B * nc, (long long)ctx->sm_count * 4);
     const size_t jet = (size_t)nslots * mat;
-    const size_t scr_steps = (size_t)grid_steps * 7 * jet;
+    const size_t scr_steps = (size_t)grid_steps * 6 * jet;
     const size_t scr_sweep = (size_t)std::max<long long>((long long)grid_sweep * std::max(ne, 1), (long long)B * (1 + ne)) * RG_BIG_SWEEP_MATS * mat;
     if (pr->ws.ensure((size_t)tasks * big_ws_step_doubles(DP, nv, ne) * cb) || pr->Qb.ensure((size_t)B * nc * mat * cb) ||
         pr->Wlb.ensure(std::max<size_t>(16, (size_t)B * nc * ne * mat * cb)) || pr->Cb.ensure((size_t)B * nc * mat * cb) ||
@@ -53,7 +53,7 @@ int big_run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int mo
         if (pr->Fdx.ensure((size_t)B * P.nx * 8)) RG_FAIL(ctx, RG_ERR_NOMEM, "device workspace allocation failed");
         iFdx = pr->Fdx.as<double>();
     }
-    BigData Bd{DP, nslots, pr->big_termM.as<double>(), pr->big_tgtM.as<double>(), nullptr, pr->dM.as<double>(), 7 * jet};
+    BigData Bd{DP, nslots, pr->big_termM.as<double>(), pr->big_tgtM.as<double>(), nullptr, pr->dM.as<double>(), 6 * jet};
     BigBufs bb{pr->ws.as<double>(), pr->Qb.as<double>(), pr->Wlb.as<double>(), pr->Cb.as<double>(), pr->Wb.as<double>(),
                pr->Gb.as<double>(), pr->G1b.as<double>(), pr->H1b.as<double>(), pr->dM.as<double>()};
     { KTimer kt(ctx, RG_K_STEPS); k_big_steps<DP><<<grid_steps, GM::NT, smem_steps, st>>>(P, Bd, dX, B, bb.ws, ctx->d_status); }

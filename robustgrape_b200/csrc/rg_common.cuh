@@ -41,6 +41,7 @@ struct DevProblem {
     int ntrig;           // trig slots: distinct arguments u = scale * v + offset of the COS/SIN/EXPI factors of H0 and error terms
     int trig_space[RG_MAX_TRIG], trig_index[RG_MAX_TRIG];
     double trig_scale[RG_MAX_TRIG], trig_offset[RG_MAX_TRIG];
+    int mixed_zero;      // 1: no error term depends on a perturbation variable (the mixed slots of dt*H itself vanish)
     int nx;              // p*N + a
     int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
     int wsm;             // complex elements stored per step matrix (d*d, or the closure pattern's nnz)
