@@ -318,6 +318,15 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_WS")) pr->force_ws = atoi(s);
     if (const char* s = getenv("RG_B2")) pr->force_b2 = atoi(s);
     if (const char* s = getenv("RG_WPP")) pr->wpp_override = atoi(s);
+    if (const char* s = getenv("RG_DENSE_ALG")) pr->force_dense_alg = atoi(s);
+    {
+        bool diag = desc->projector != nullptr && pr->has_target;
+        for (int j = 0; j < d && diag; ++j)
+            for (int i = 0; i < d; ++i)
+                if (i != j && P0[i + d * j] != 0.0) { diag = false; break; }
+        for (auto& en : te) if (en.row != en.col) diag = false;
+        pr->diag_alg = diag ? 1 : 0;
+    }
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
     if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS) {
         const int npos = d * (d + 1) / 2;

@@ -10,11 +10,19 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
               double scale0, double scale0T, int do_grad) {
     rg_ctx* ctx = pr->ctx;
     const size_t smem = fq_smem_bytes(D, b2_nblocks(D, UM), P.nterms, pr->tri.nent);
+    const bool da = pr->diag_alg && !pr->force_dense_alg;
     if (!pr->fq_ctas[0]) {
-        int rc = set_smem(ctx, k_fused_q<D, UM, false>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, true>, smem); if (rc) return rc;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[0], k_fused_q<D, UM, false>, 128, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[1], k_fused_q<D, UM, true>, 128, smem);
+        int rc = set_smem(ctx, k_fused_q<D, UM, false, false>, smem); if (rc) return rc;
+        rc = set_smem(ctx, k_fused_q<D, UM, true, false>, smem); if (rc) return rc;
+        rc = set_smem(ctx, k_fused_q<D, UM, false, true>, smem); if (rc) return rc;
+        rc = set_smem(ctx, k_fused_q<D, UM, true, true>, smem); if (rc) return rc;
+        if (da) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[0], k_fused_q<D, UM, false, true>, 128, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[1], k_fused_q<D, UM, true, true>, 128, smem);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[0], k_fused_q<D, UM, false, false>, 128, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[1], k_fused_q<D, UM, true, false>, 128, smem);
+        }
         pr->fq_ctas[0] = std::max(1, pr->fq_ctas[0]); pr->fq_ctas[1] = std::max(1, pr->fq_ctas[1]);
     }
     // warps per pulse: cost = waves * (sweep steps per lane + fixed scan/algebra overhead of ~24 sweep steps)
@@ -31,10 +39,13 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     const int ppc = 4 / wpp;
     dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? P.e : 1);
     KTimer kt(ctx, err_role ? RG_K_GRAD_ERR : RG_K_GRAD);
-    if (err_role)
-        k_fused_q<D, UM, true><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
-    else
-        k_fused_q<D, UM, false><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+    if (err_role) {
+        if (da) k_fused_q<D, UM, true, true><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+        else k_fused_q<D, UM, true, false><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+    } else {
+        if (da) k_fused_q<D, UM, false, true><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+        else k_fused_q<D, UM, false, false><<<grid, 128, smem, ctx->stream>>>(P, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status);
+    }
     return RG_OK;
 }
 }  // namespace

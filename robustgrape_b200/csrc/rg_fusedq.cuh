@@ -166,13 +166,96 @@ __host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int n
     return staged_plan_bytes(nterms, nent, d) + 4 * slot * sizeof(cplx);
 }
 
+
+// ---- fidelity algebra for a diagonal projector and a diagonal target (the CZ problems: diag(1,2,1,0,0), diag(1, e^{i theta}, ...)) ----
+// With P0 = diag(p), P = diag(pi), U0 = diag(u0) every product of src/FidelityCalculations.jl:47-114 is elementwise:
+//   tau   = sum_i p_i conj(u0_i) U_ii                       tr12 = sum_ij p_i pi_j |u0_i|^2 |U_ij|^2
+//   K_ij  = 2 pi_i p_j |u0_j|^2 conj(U_ji) + 2 conj(tau) p_i conj(u0_i) delta_ij
+//   K'_ij = K_ij[U -> E] - 2 (1 + D) p_i conj(E_ji) ,       tee  = sum_i p_i sum_k |E_ki|^2
+// (derived from the dense sequence in fid_algebra; tests compare the two paths).  U is block diagonal -- NB quaternion blocks plus
+// the identity on untouched levels (zero there for E) -- so every lane forms proj(K) of its blocks itself; no serial section.
+template <int D, unsigned UMASK, bool ERR>
+struct FQDiag {
+    static constexpr int NB = b2_nblocks(D, UMASK);
+    // entry (i, j) of the block-diagonal matrix held as quaternions; i, j compile-time after unrolling
+    static __device__ __forceinline__ cplx entry(const QS<NB>& u, int n, int which) {      // which: 0 lolo, 1 lohi, 2 hilo, 3 hihi
+        return which == 0 ? u.a[n] : which == 1 ? u.b[n] : which == 2 ? cmk(-u.b[n].x, u.b[n].y) : cconj(u.a[n]);
+    }
+    static __device__ __forceinline__ cplx tau(const QS<NB>& u, const cplx* u0, const double* pw) {
+        cplx t = cmk(0.0, 0.0);
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            cfma_conj(t, cscale(u0[lo], pw[lo]), u.a[n]);
+            cfma_conj(t, cscale(u0[hi], pw[hi]), cconj(u.a[n]));
+        }
+        if constexpr (!ERR) {
+#pragma unroll
+            for (int l = 0; l < D; ++l)
+                if (b2_partner(D, UMASK, l) < 0) { t.x += pw[l] * u0[l].x; t.y -= pw[l] * u0[l].y; }      // U_ll = 1
+        }
+        return t;
+    }
+    // quaternion projection of the co-state seed on every block
+    static __device__ __forceinline__ void seed(const QS<NB>& u, const cplx* u0, const double* pw, cplx tauv, double Dt, QS<NB>& kq) {
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            const double plo = pw[lo], phi = pw[hi], pilo = plo != 0.0 ? 1.0 : 0.0, pihi = phi != 0.0 ? 1.0 : 0.0;
+            const double alo = u0[lo].x * u0[lo].x + u0[lo].y * u0[lo].y, ahi = u0[hi].x * u0[hi].x + u0[hi].y * u0[hi].y;
+            const cplx ct = cconj(tauv);
+            // K_ij = 2 pi_i p_j |u0_j|^2 conj(U_ji) + 2 conj(tau) p_i conj(u0_i) delta_ij
+            cplx k11 = cscale(cconj(entry(u, n, 0)), 2.0 * pilo * plo * alo);
+            cplx k12 = cscale(cconj(entry(u, n, 2)), 2.0 * pilo * phi * ahi);
+            cplx k21 = cscale(cconj(entry(u, n, 1)), 2.0 * pihi * plo * alo);
+            cplx k22 = cscale(cconj(entry(u, n, 3)), 2.0 * pihi * phi * ahi);
+            k11 = cadd(k11, cscale(cmul(ct, cconj(u0[lo])), 2.0 * plo));
+            k22 = cadd(k22, cscale(cmul(ct, cconj(u0[hi])), 2.0 * phi));
+            if constexpr (ERR) {      // - 2 (1 + D) p_i conj(E_ji)
+                const double f = 2.0 * (1.0 + Dt);
+                k11 = csub(k11, cscale(cconj(entry(u, n, 0)), f * plo)); k12 = csub(k12, cscale(cconj(entry(u, n, 2)), f * plo));
+                k21 = csub(k21, cscale(cconj(entry(u, n, 1)), f * phi)); k22 = csub(k22, cscale(cconj(entry(u, n, 3)), f * phi));
+            }
+            kq.a[n] = cmk(0.5 * (k11.x + k22.x), 0.5 * (k11.y - k22.y));            // (k11 + conj k22) / 2
+            kq.b[n] = cmk(0.5 * (k12.x - k21.x), 0.5 * (k12.y + k21.y));            // (k12 - conj k21) / 2
+        }
+    }
+    // sum_ij p_i pi_j w_i |U_ij|^2 with w_i = |u0_i|^2 (tr12) or any per-row weight; and sum_i p_i sum_k |E_ki|^2 (tee)
+    static __device__ __forceinline__ double rowsum(const QS<NB>& u, const double* roww, const double* pw) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            const double na = u.a[n].x * u.a[n].x + u.a[n].y * u.a[n].y, nb = u.b[n].x * u.b[n].x + u.b[n].y * u.b[n].y;
+            const double pilo = pw[lo] != 0.0 ? 1.0 : 0.0, pihi = pw[hi] != 0.0 ? 1.0 : 0.0;
+            s += pw[lo] * roww[lo] * (pilo * na + pihi * nb) + pw[hi] * roww[hi] * (pilo * nb + pihi * na);
+        }
+        if constexpr (!ERR) {
+#pragma unroll
+            for (int l = 0; l < D; ++l)
+                if (b2_partner(D, UMASK, l) < 0) s += pw[l] * roww[l] * (pw[l] != 0.0 ? 1.0 : 0.0);
+        }
+        return s;
+    }
+    static __device__ __forceinline__ double tee(const QS<NB>& u, const double* pw) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+            const double na = u.a[n].x * u.a[n].x + u.a[n].y * u.a[n].y, nb = u.b[n].x * u.b[n].x + u.b[n].y * u.b[n].y;
+            s += (pw[lo] + pw[hi]) * (na + nb);            // column i of E: |E_lo,i|^2 + |E_hi,i|^2 = |a|^2 + |b|^2 for both columns
+        }
+        return s;
+    }
+};
+
 #ifndef RG_FQ_CTAS
 #define RG_FQ_CTAS 3
 #endif
 
 // ERR = false: fidelity role.   Fout[b] = F (fmode 0) or 1 - F (fmode 1);  out[b*nx + ...] = scale0 * dF/dx  (x_add target part * scale0T)
 // ERR = true : role of error source e = blockIdx.y.  Fout[b*ne + e] = F_d2err[e];  out[(b*ne+e)*nx + ...] = dF_d2err[e]/dx
-template <int D, unsigned UMASK, bool ERR>
+template <int D, unsigned UMASK, bool ERR, bool DA>
 __global__ void __launch_bounds__(128, ERR ? 2 : RG_FQ_CTAS)
 k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
           int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int* __restrict__ status) {
@@ -255,47 +338,130 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     }
     // the last lane of the pulse holds C_N (and W_N): publish them, and the dense matrix the algebra starts from
     if (t == 32 * wpp - 1) {
-        cplx* mU = alg + 2 * DD;
-        for (int i = 0; i < DD; ++i) mU[i] = cmk(0.0, 0.0);
-        if constexpr (!ERR) {
-#pragma unroll
-            for (int l = 0; l < D; ++l)
-                if (b2_partner(D, UMASK, l) < 0) mU[l + D * l] = cmk(1.0, 0.0);      // untouched levels: U(l,l) = 1
-        }
 #pragma unroll
         for (int n = 0; n < NB; ++n) {
-            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
             finC[2 * n] = q.a[n]; finC[2 * n + 1] = q.b[n];
             if constexpr (ERR) { finC[2 * NB + 2 * n] = vq.a[n]; finC[2 * NB + 2 * n + 1] = vq.b[n]; }
-            const cplx a = ERR ? cscale(vq.a[n], P.inv_eps) : q.a[n], bb = ERR ? cscale(vq.b[n], P.inv_eps) : q.b[n];
-            mU[lo + D * lo] = a; mU[lo + D * hi] = bb;
-            mU[hi + D * lo] = cmk(-bb.x, bb.y); mU[hi + D * hi] = cconj(a);
+        }
+        if constexpr (!DA) {
+            cplx* mU = alg + 2 * DD;
+            for (int i = 0; i < DD; ++i) mU[i] = cmk(0.0, 0.0);
+            if constexpr (!ERR) {
+#pragma unroll
+                for (int l = 0; l < D; ++l)
+                    if (b2_partner(D, UMASK, l) < 0) mU[l + D * l] = cmk(1.0, 0.0);      // untouched levels: U(l,l) = 1
+            }
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+                const cplx a = ERR ? cscale(vq.a[n], P.inv_eps) : q.a[n], bb = ERR ? cscale(vq.b[n], P.inv_eps) : q.b[n];
+                mU[lo + D * lo] = a; mU[lo + D * hi] = bb;
+                mU[hi + D * lo] = cmk(-bb.x, bb.y); mU[hi + D * hi] = cconj(a);
+            }
+        }
+    }
+    // diagonal algebra: the first warp evaluates the target diagonal u0(x_add) and its finite differences in x_add
+    cplx* tcs = alg;                                   // [ntt]               term coefficients
+    cplx* dtc = alg + DD;                              // [a][ntt]            their differences / eps
+    cplx* u0s = alg + DD * (1 + RG_MAX_ADD);           // [D]
+    cplx* v0s = u0s + D;                               // [a][D]
+    double* pws = reinterpret_cast<double*>(v0s + RG_MAX_ADD * D);      // [D] projector diagonal
+    if constexpr (DA) {
+        if (wip == 0) {
+            EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
+            for (int tt = lane; tt < P.ntt; tt += 32) {
+                cplx bs, dl;
+                term_coef(P.tterms[tt], ec, RG_S_NONE, 0, 0.0, bs, dl);
+                tcs[tt] = bs;
+                for (int j = 0; j < P.a; ++j) {
+                    const double hh = __dsub_rn(__dadd_rn(xadd[j], P.eps), xadd[j]);
+                    term_coef(P.tterms[tt], ec, RG_S_ADD, j, hh, bs, dl);
+                    dtc[j * DD + tt] = cscale(dl, P.inv_eps);
+                }
+            }
+            __syncwarp();
+            if (lane < D) {
+                cplx u = cmk(0.0, 0.0);
+                for (int en = 0; en < P.ntent; ++en)
+                    if (P.tents[en].row == lane && P.tents[en].col == lane) cfma(u, tcs[P.tents[en].term], cmk(P.tents[en].vr, P.tents[en].vi));
+                u0s[lane] = u;
+                for (int j = 0; j < P.a; ++j) {
+                    cplx vv = cmk(0.0, 0.0);
+                    for (int en = 0; en < P.ntent; ++en)
+                        if (P.tents[en].row == lane && P.tents[en].col == lane) cfma(vv, dtc[j * DD + P.tents[en].term], cmk(P.tents[en].vr, P.tents[en].vi));
+                    v0s[j * D + lane] = vv;
+                }
+                pws[lane] = P.P0raw[lane + D * lane];
+            }
         }
     }
     __syncthreads();
-    // ---- 3. fidelity algebra by D lanes of the pulse's first warp
-    if (wip == 0 && lane < D) {
-        constexpr unsigned amask = (1u << D) - 1u;
-        const double Fval = fid_algebra<D>(P, alg, xadd, ERR ? 1 + es : 0, lane, amask, addT, true);
-        if (live && lane == 0) {
-            if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
-            else Fout[(size_t)b * ne + es] = Fval;
+    // ---- 3. fidelity algebra
+    Q kq;
+    if constexpr (DA) {
+        Q un;                                           // C_N, or E = W_N / eps
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            un.a[n] = ERR ? cscale(finC[2 * NB + 2 * n], P.inv_eps) : finC[2 * n];
+            un.b[n] = ERR ? cscale(finC[2 * NB + 2 * n + 1], P.inv_eps) : finC[2 * n + 1];
         }
+        typedef FQDiag<D, UMASK, ERR> DG;
+        const cplx tauv = DG::tau(un, u0s, pws);
+        DG::seed(un, u0s, pws, tauv, P.Dtr, kq);
+        if (t == 0) {
+            const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
+            double w2[D];
+#pragma unroll
+            for (int l = 0; l < D; ++l) w2[l] = u0s[l].x * u0s[l].x + u0s[l].y * u0s[l].y;
+            const double tr12 = DG::rowsum(un, w2, pws);
+            double Fval = (tr12 + tauv.x * tauv.x + tauv.y * tauv.y) / DD1;
+            if constexpr (ERR) Fval = 2.0 * (tr12 - (1.0 + Dt) * DG::tee(un, pws) + tauv.x * tauv.x + tauv.y * tauv.y) / DD1;
+            if (live) {
+                if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
+                else Fout[(size_t)b * ne + es] = Fval;
+            }
+            for (int j = 0; j < P.a; ++j) {             // target-derivative part of the x_add[j] entry (:35-40,72-74,102-109)
+                double wj[D];
+                cplx t3 = cmk(0.0, 0.0);
+#pragma unroll
+                for (int l = 0; l < D; ++l) {
+                    const cplx vl = v0s[j * D + l];
+                    wj[l] = 2.0 * (vl.x * u0s[l].x + vl.y * u0s[l].y);          // 2 Re(conj(v_l) u0_l)
+                }
+                // t3 = sum_i p_i conj(v_i) U_ii: tau() with v in place of u0
+                t3 = DG::tau(un, v0s + j * D, pws);
+                const double s12 = DG::rowsum(un, wj, pws);
+                addT[j] = (ERR ? 2.0 : 1.0) * (s12 + 2.0 * (tauv.x * t3.x + tauv.y * t3.y)) / DD1;
+            }
+        }
+        __syncthreads();                                // addT visible to the final reduction
+    } else {
+        if (wip == 0 && lane < D) {
+            constexpr unsigned amask = (1u << D) - 1u;
+            const double Fval = fid_algebra<D>(P, alg, xadd, ERR ? 1 + es : 0, lane, amask, addT, true);
+            if (live && lane == 0) {
+                if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
+                else Fout[(size_t)b * ne + es] = Fval;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (!do_grad) { if (Kmax == 99) atomicOr(status, 2); return; }          // F / F_d2err only
     // ---- 4. co-states at the end of this lane's chunk
     Q g, h;
     {
-        const cplx* mK = alg + 9 * DD;
-        Q kq, cn;
+        Q cn;
 #pragma unroll
-        for (int n = 0; n < NB; ++n) {
-            const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
-            const cplx m11 = mK[lo + D * lo], m12 = mK[lo + D * hi], m21 = mK[hi + D * lo], m22 = mK[hi + D * hi];
-            kq.a[n] = cmk(0.5 * (m11.x + m22.x), 0.5 * (m11.y - m22.y));            // (m11 + conj m22) / 2
-            kq.b[n] = cmk(0.5 * (m12.x - m21.x), 0.5 * (m12.y + m21.y));            // (m12 - conj m21) / 2
-            cn.a[n] = finC[2 * n]; cn.b[n] = finC[2 * n + 1];
+        for (int n = 0; n < NB; ++n) { cn.a[n] = finC[2 * n]; cn.b[n] = finC[2 * n + 1]; }
+        if constexpr (!DA) {
+            const cplx* mK = alg + 9 * DD;
+#pragma unroll
+            for (int n = 0; n < NB; ++n) {
+                const int lo = QBlk<D, UMASK>::lo(n), hi = QBlk<D, UMASK>::hi(n);
+                const cplx m11 = mK[lo + D * lo], m12 = mK[lo + D * hi], m21 = mK[hi + D * lo], m22 = mK[hi + D * hi];
+                kq.a[n] = cmk(0.5 * (m11.x + m22.x), 0.5 * (m11.y - m22.y));            // (m11 + conj m22) / 2
+                kq.b[n] = cmk(0.5 * (m12.x - m21.x), 0.5 * (m12.y + m21.y));            // (m12 - conj m21) / 2
+            }
         }
         Q bs; qs_muladj(bs, cn, q);                                                  // B_t = C_N P_t^dag
         qs_mul(g, kq, bs);

@@ -541,6 +541,12 @@ def test_fused_quaternion_path_shapes(gpu_ctx, monkeypatch, N, B):
     for k, u, v in zip(NAMES, new, old):
         assert relmax(u, v) < 1e-11, (k, relmax(u, v))
     assert np.array_equal(new[0], new_nograd[0]) and np.array_equal(new[2], new_nograd[2])
+    # the fused kernel's elementwise (diagonal projector / target) fidelity algebra against its dense fidelity algebra
+    monkeypatch.delenv("RG_WS")
+    monkeypatch.setenv("RG_DENSE_ALG", "1")
+    dense_alg = rg.calculate_fidelity_and_derivatives_batch(cz_problem(N, 7.613 * max(N, 20) / 1000, ("amp",)), X)
+    for k, u, v in zip(NAMES, new, dense_alg):
+        assert relmax(u, v) < 1e-12, (k, relmax(u, v))
 
 
 def test_block2_large_step_norm(gpu_ctx):
