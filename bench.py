@@ -9,9 +9,9 @@ without host regularisation) of every pulse of the batch: 8192 random-init pulse
 5-level symmetric-blockaded Rydberg CZ problem (examples/time_optimal_cz.jl) per GPU. Pulses are independent, so for
 N > 1 they are sharded over the ranks with no collective inside an evaluation; each step ends with an all-gather of every
 rank's [cost | grad] block (peer-memory copies by default, `--gather nccl` for ncclAllGather).
-`--scaling weak` (default): the multi-start batch grows with the box, 8192 pulses per GPU.
-`--scaling strong`: the 8192-pulse batch is fixed and split over the ranks (also measured and reported under
-`extra.strong_scaling` when N > 1).
+`--scaling strong` (default): the 8192-pulse batch of BASELINE.json configs[3] is fixed and sharded over the ranks.
+`--scaling weak`: the multi-start batch grows with the box, 8192 pulses per GPU (also measured and reported under
+`extra.weak_scaling` when N > 1).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -328,8 +328,9 @@ def main():
     ap.add_argument("--dense-ntimes", type=int, default=10000)
     ap.add_argument("--dense-norm", type=float, default=2.4, help="max_k ||dt H(k)||_1 of the dense workload (SURVEY 8d: 2.1 ... 5.4)")
     ap.add_argument("--dense-batch", type=int, default=1)
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = --batch pulses per GPU (default), strong = --batch pulses in total")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = the --batch pulses of BASELINE.json configs[3] sharded over the ranks; "
+                         "weak = --batch pulses per GPU (reported under extra.weak_scaling)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
                     help="N > 1: how the per-rank [cost|grad] blocks are gathered each step")
     args = ap.parse_args()
@@ -410,12 +411,18 @@ def main():
             out_alls = [torch.empty(world * blk, dtype=torch.float64, device=dev) for _ in range(2)]
         pending = [None, None]
         step_no = [0]
+        # cross-rank completion of the peer gather: after this rank's pushes of a step are done (a side stream waits for their
+        # event) a one-element NCCL all-reduce is issued asynchronously; when it completes, every rank's block of that step has
+        # landed in every rank's buffer.  It is waited for before the buffer is reused (two steps later) and in drain(), i.e.
+        # inside the timed region, off the evaluation stream.
+        bstream = torch.cuda.Stream(device=dev) if pg is not None else None
+        flag = torch.zeros(1, dtype=torch.float32, device=dev) if pg is not None else None
 
         def step():
             i = step_no[0] & 1
             step_no[0] += 1
             if pending[i] is not None:
-                pending[i].wait()                                  # buffer i is free again (its gather finished)
+                pending[i].wait()                                  # buffer i is free again (its gather finished on every rank)
                 pending[i] = None
             if pg is not None:
                 pg.wait(i)
@@ -426,6 +433,9 @@ def main():
                 pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
             elif pg is not None:
                 pg.push(ol.data_ptr(), i)
+                pg.wait_on(i, bstream.cuda_stream)
+                with torch.cuda.stream(bstream):
+                    pending[i] = dist.all_reduce(flag, async_op=True)
 
         def drain():
             for i in (0, 1):

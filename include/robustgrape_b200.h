@@ -169,6 +169,9 @@ int rg_peer_buffer_destroy(rg_ctx* ctx, void* dptr);
 int rg_gather_to_peers(rg_ctx* ctx, const void* src, uint64_t bytes, int32_t npeers, void* const* peer_base,
                        uint64_t dst_offset, int32_t slot, int32_t mode);
 int rg_gather_wait(rg_ctx* ctx, int32_t slot);
+/* Same wait, on a caller-chosen stream (cudaStream_t as void*): used to order a cross-rank barrier after this rank's pushes
+ * without stalling the evaluation stream. */
+int rg_gather_wait_on(rg_ctx* ctx, int32_t slot, void* cuda_stream);
 
 /* FP64 peak microbenchmarks (DFMA loop, DMMA m8n8k4 loop) on the context device: TFLOP/s. */
 int rg_measure_fp64_peak(rg_ctx* ctx, double seconds, double* dfma_tflops, double* dmma_tflops);

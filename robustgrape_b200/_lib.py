@@ -80,6 +80,7 @@ SIGNATURES = {
     "rg_peer_buffer_destroy": (C.c_int, [_vp, _vp]),
     "rg_gather_to_peers": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int32, C.POINTER(_vp), C.c_uint64, C.c_int32, C.c_int32]),
     "rg_gather_wait": (C.c_int, [_vp, C.c_int32]),
+    "rg_gather_wait_on": (C.c_int, [_vp, C.c_int32, _vp]),
     "rg_measure_fp64_peak": (C.c_int, [_vp, C.c_double, _dp, _dp]),
 }
 
@@ -178,6 +179,9 @@ class Context:
 
     def gather_wait(self, slot=0):
         self.check(self.lib.rg_gather_wait(self.handle, int(slot)))
+
+    def gather_wait_on(self, slot, cuda_stream):
+        self.check(self.lib.rg_gather_wait_on(self.handle, int(slot), _vp(cuda_stream)))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -250,7 +250,7 @@ struct FQDiag {
 };
 
 #ifndef RG_FQ_CTAS
-#define RG_FQ_CTAS 3
+#define RG_FQ_CTAS 4          // 128-register cap: measured on B200 equal at 8192 pulses (0.514 vs 0.510 ms), 18-23 % faster at 1024-2048
 #endif
 
 // ERR = false: fidelity role.   Fout[b] = F (fmode 0) or 1 - F (fmode 1);  out[b*nx + ...] = scale0 * dF/dx  (x_add target part * scale0T)

@@ -113,6 +113,15 @@ extern "C" int rg_gather_to_peers(rg_ctx* c, const void* src, uint64_t bytes, in
     return RG_OK;
 }
 
+// Make `cuda_stream` (any stream of this device, e.g. the one a collective barrier is issued on) wait for the gather last issued on
+// `slot`: cross-rank completion = every rank's outgoing copies done + a barrier, without touching the evaluation stream.
+extern "C" int rg_gather_wait_on(rg_ctx* c, int32_t slot, void* cuda_stream) {
+    if (!c || slot < 0 || slot > 1) return RG_ERR_INVALID;
+    if (!c->gather_pending[slot]) return RG_OK;
+    CU(c, cudaStreamWaitEvent((cudaStream_t)cuda_stream, c->ev_gather[slot], 0));
+    return RG_OK;
+}
+
 extern "C" int rg_gather_wait(rg_ctx* c, int32_t slot) {
     if (!c || slot < 0 || slot > 1) return RG_ERR_INVALID;
     if (!c->gather_pending[slot]) return RG_OK;

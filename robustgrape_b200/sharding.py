@@ -79,6 +79,10 @@ class PeerGather:
     def wait(self, slot):
         self.ctx.gather_wait(slot)
 
+    def wait_on(self, slot, cuda_stream):
+        """`cuda_stream` waits for this rank's pushes of `slot` (then a barrier there = cross-rank completion)."""
+        self.ctx.gather_wait_on(slot, cuda_stream)
+
     def view(self, buf, device):
         """torch view (no copy) of this rank's gathered buffer `buf`: world*block doubles."""
         import torch
