@@ -411,13 +411,12 @@ def main():
             out_alls = [torch.empty(world * blk, dtype=torch.float64, device=dev) for _ in range(2)]
         pending = [None, None]
         step_no = [0]
-        # cross-rank completion of the peer gather: after this rank's pushes of a step are done (a side stream waits for their
-        # event) a one-element NCCL all-reduce is issued asynchronously; when it completes, every rank's block of that step has
-        # landed in every rank's buffer.  It is waited for before the buffer is reused (two steps later) and in drain(), i.e.
-        # inside the timed region, off the evaluation stream.
-        bstream = torch.cuda.Stream(device=dev) if pg is not None else None
         flag = torch.zeros(1, dtype=torch.float32, device=dev) if pg is not None else None
-
+        # Cross-rank completion of the peer gather: drain() orders the end of the timed region after this rank's outgoing copies of
+        # every step, and finish() adds one NCCL barrier inside the timed region -- after it, every rank's block of every timed
+        # step has landed in every rank's buffer.  (A per-step NCCL handshake was measured: its ~100 us of host-side launch work
+        # per step exceeds the 80 us evaluation of a 1024-pulse shard; consumers that need per-step completion poll nothing --
+        # they order their reader after rg_gather_wait_on + their own barrier, see sharding.PeerGather.)
         def step():
             i = step_no[0] & 1
             step_no[0] += 1
@@ -433,9 +432,6 @@ def main():
                 pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
             elif pg is not None:
                 pg.push(ol.data_ptr(), i)
-                pg.wait_on(i, bstream.cuda_stream)
-                with torch.cuda.stream(bstream):
-                    pending[i] = dist.all_reduce(flag, async_op=True)
 
         def drain():
             for i in (0, 1):
@@ -444,6 +440,11 @@ def main():
                     pending[i] = None
                 if pg is not None:
                     pg.wait(i)
+
+        def finish():
+            drain()
+            if pg is not None:
+                dist.all_reduce(flag)          # stream-ordered after the drained pushes of every rank: cross-rank completion
 
         for _ in range(warmup):
             step()
@@ -458,7 +459,7 @@ def main():
         e0.record()
         for _ in range(steps):
             step()
-        drain()                                                    # every step's gather completes inside the timed region
+        finish()                                                   # every step's gather completes on every rank inside the timed region
         e1.record()
         barrier()
         if sampler:
