@@ -78,6 +78,8 @@ typedef struct rg_problem_desc {
     int32_t ntable_cols;
     const double* table;      /* ntimes x ntable_cols real, column-major; may be NULL */
     int32_t hermitian;        /* 1: H0 + error terms Hermitian for real variables (unitary propagators) */
+    int32_t hstack;           /* 1: H-stack problem -- H0 / Herror / target_unitary are opaque closures (src/Types.jl:13,35,55)
+                                 evaluated by the caller; nterms = ntarget_terms = 0; use the *_from_hstack entry points    */
 } rg_problem_desc;
 
 typedef struct rg_ctx rg_ctx;
@@ -128,6 +130,20 @@ int rg_cost_and_grad_batch_dev(rg_problem* prob, int32_t B, const double* dX, co
  * U_derr_dx_add (d,d,a,e); complex interleaved.  Output pointers may be NULL.                    */
 int rg_unitary_and_derivatives(rg_problem* prob, const double* x, double* U, double* U_dx,
                                double* U_dx_add, double* U_derr, double* U_derr_dx, double* U_derr_dx_add);
+
+/* Closure problems: the caller evaluates its closures into the Hamiltonians whose exponentials the reference
+ * forms (src/UnitaryCalculations.jl:45-97) and the library does everything after that (exponentials, scans, contractions,
+ * reductions).  nvar = nparam + nb_additional_param, n_exp = 1 + 2 nvar + nerr (2 + nvar).
+ *   Hstack (d, d, n_exp, N) complex: per step, in this order,
+ *       H0(x) | H0(x + eps e_v), v < nvar | H0(x + eps2 e_v) | H0(x) + Herr_e(x, eps), e < nerr | H0(x) + Herr_e(x, eps2) |
+ *       H0(x + eps2 e_v) + Herr_e(x + eps2 e_v, eps2)   (index e * nvar + v)
+ *     where e_v perturbs main parameter v of this step for v < nparam and additional parameter v - nparam otherwise;
+ *   Tstack (d, d, 1 + nb_additional_param) complex: target_unitary(x_add) | target_unitary(x_add + eps e_j).
+ * Outputs as rg_fidelity_and_derivatives_batch with B = 1 / rg_unitary_and_derivatives.  ndim <= 10.                          */
+int rg_fidelity_and_derivatives_from_hstack(rg_problem* prob, const double* Hstack, const double* Tstack,
+                                            double* F, double* F_dx, double* F_d2err, double* F_d2err_dx);
+int rg_unitary_and_derivatives_from_hstack(rg_problem* prob, const double* Hstack, double* U, double* U_dx, double* U_dx_add,
+                                           double* U_derr, double* U_derr_dx, double* U_derr_dx_add);
 
 /* calculate_interaction_error_operators (src/UnitaryCalculations.jl:180-204): O (d,d,N,e) complex. */
 int rg_interaction_error_operators(rg_problem* prob, const double* x, double* O);

@@ -45,7 +45,7 @@ class rg_problem_desc(C.Structure):
                 ("ntarget_terms", C.c_int32), ("target_terms", C.POINTER(rg_term)),
                 ("projector", C.POINTER(C.c_double)),
                 ("ntable_cols", C.c_int32), ("table", C.POINTER(C.c_double)),
-                ("hermitian", C.c_int32)]
+                ("hermitian", C.c_int32), ("hstack", C.c_int32)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -68,6 +68,8 @@ SIGNATURES = {
     "rg_fidelity_and_derivatives_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "rg_cost_and_grad_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
     "rg_unitary_and_derivatives": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_fidelity_and_derivatives_from_hstack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_unitary_and_derivatives_from_hstack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_interaction_error_operators": (C.c_int, [_vp, _vp, _vp]),
     "rg_fidelity_response": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "rg_fidelity_response_fft": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp]),
@@ -363,3 +365,144 @@ class Problem:
         self._keep_coeff = coeff
         self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch_dev(h, B, _vp(dX_ptr), _ptr(coeff) if self.nerr else None,
                                                              _vp(dcost_ptr), _vp(dgrad_ptr)))
+
+
+class HStackProblem:
+    """Closure problem (reference src/Types.jl:13,35,55: H0 / Herror / target_unitary are arbitrary callables).  The closures are
+    evaluated here, on the host, into the stack of Hamiltonians whose exponentials the reference forms
+    (src/UnitaryCalculations.jl:45-97); everything after that -- exponentials, scans, contractions, fidelity reductions --
+    runs in the CUDA library (rg_*_from_hstack).  Finite differences of host-evaluated closures carry the reference's own
+    FP64 noise floor (the perturbed and unperturbed Hamiltonians are subtracted after rounding), unlike descriptor problems."""
+
+    def __init__(self, problem, ctx=None):
+        from .types import FidelityRobustGRAPEProblem, UnitaryRobustGRAPEProblem
+        self.ctx = ctx or default_context()
+        if isinstance(problem, FidelityRobustGRAPEProblem):
+            self.up, self.fp = problem.unitary_problem, problem
+        elif isinstance(problem, UnitaryRobustGRAPEProblem):
+            self.up, self.fp = problem, None
+        else:
+            raise TypeError("expected a UnitaryRobustGRAPEProblem or FidelityRobustGRAPEProblem")
+        up = self.up
+        if up.ndim > 10:
+            raise RGError(RG_ERR_UNSUPPORTED, "closure (H-stack) problems are implemented for ndim <= 10")
+        self.ndim, self.ntimes = int(up.ndim), int(up.ntimes)
+        self.na, self.nerr = int(up.nb_additional_param), len(up.error_sources)
+        self._handles = {}
+        self._keep = []
+
+    def _handle(self, p, hermitian):
+        key = (p, hermitian)
+        if key not in self._handles:
+            up = self.up
+            desc = rg_problem_desc()
+            desc.ndim, desc.ntimes, desc.nparam = self.ndim, self.ntimes, p
+            desc.nb_additional_param, desc.nerr = self.na, self.nerr
+            desc.t0, desc.eps, desc.eps2 = float(up.t0), float(up.eps), float(up.eps2)
+            desc.nterms, desc.ntarget_terms = 0, 0
+            if self.fp is not None:
+                proj = np.asfortranarray(np.asarray(self.fp.projector, dtype=np.float64))
+                self._keep.append(proj)
+                desc.projector = proj.ctypes.data_as(_dp)
+            desc.hermitian, desc.hstack = (1 if hermitian else 0), 1
+            h = _vp()
+            self.ctx.check(self.ctx.lib.rg_problem_create(self.ctx.handle, C.byref(desc), C.byref(h)))
+            self._handles[key] = h
+        return self._handles[key]
+
+    def stacks(self, x):
+        """(Hstack (d,d,n_exp,N), Tstack (d,d,1+a) or None, p) for pulse x, with the reference's perturbation arithmetic
+        (x + eps, evaluate, reset: src/UnitaryCalculations.jl:50-55,58-63,76-84,88-96; target: src/FidelityCalculations.jl:32-40)."""
+        up = self.up
+        x = np.asarray(x, dtype=np.float64)
+        N, d, a, ne = self.ntimes, self.ndim, self.na, self.nerr
+        nmain = len(x) - a
+        if nmain < 0 or nmain % N != 0:
+            raise AssertionError("Control parameter size must be a multiple of time steps")
+        p = nmain // N
+        nvar = p + a
+        nexp = 1 + 2 * nvar + ne * (2 + nvar)
+        xm = x[:nmain].reshape((p, N), order="F")
+        xa = x[nmain:].copy()
+        eps, eps2 = float(up.eps), float(up.eps2)
+        Hs = np.zeros((d, d, nexp, N), dtype=np.complex128, order="F")
+        H0 = up.H0
+
+        def pert(k, v, h):
+            xk, xad = xm[:, k].copy(), xa.copy()
+            if v < p:
+                xk[v] += h
+            else:
+                xad[v - p] += h
+            return xk, xad
+
+        for k in range(N):
+            xk = xm[:, k].copy()
+            base = np.asarray(H0(k + 1, xk, xa), dtype=np.complex128)
+            Hs[:, :, 0, k] = base
+            for v in range(nvar):
+                Hs[:, :, 1 + v, k] = H0(k + 1, *pert(k, v, eps))
+                Hs[:, :, 1 + nvar + v, k] = H0(k + 1, *pert(k, v, eps2))
+            for e, src in enumerate(up.error_sources):
+                Hs[:, :, 1 + 2 * nvar + e, k] = base + np.asarray(src.Herror(k + 1, xk, xa, eps))
+                Hs[:, :, 1 + 2 * nvar + ne + e, k] = base + np.asarray(src.Herror(k + 1, xk, xa, eps2))
+                for v in range(nvar):
+                    xk2, xa2 = pert(k, v, eps2)
+                    Hs[:, :, 1 + 2 * nvar + 2 * ne + e * nvar + v, k] = np.asarray(H0(k + 1, xk2, xa2)) + np.asarray(src.Herror(k + 1, xk2, xa2, eps2))
+        Ts = None
+        if self.fp is not None:
+            Ts = np.zeros((d, d, 1 + a), dtype=np.complex128, order="F")
+            Ts[:, :, 0] = self.fp.target_unitary(xa)
+            for j in range(a):
+                xa2 = xa.copy()
+                xa2[j] += eps
+                Ts[:, :, 1 + j] = self.fp.target_unitary(xa2)
+        return Hs, Ts, p
+
+    @staticmethod
+    def _hermitian(Hs):
+        return bool(np.abs(Hs - np.conj(np.swapaxes(Hs, 0, 1))).max() <= 1e-13 * max(1.0, np.abs(Hs).max()))
+
+    def fidelity_and_derivatives(self, x):
+        Hs, Ts, p = self.stacks(x)
+        h = self._handle(p, self._hermitian(Hs))
+        nx = len(x)
+        F = np.zeros(1)
+        Fdx = np.zeros((nx, 1), order="F")
+        F2 = np.zeros((self.nerr, 1), order="F")
+        F2dx = np.zeros((nx, self.nerr, 1), order="F")
+        self.ctx.check(self.ctx.lib.rg_fidelity_and_derivatives_from_hstack(h, _ptr(Hs), _ptr(Ts), _ptr(F), _ptr(Fdx), _ptr(F2), _ptr(F2dx)))
+        return float(F[0]), Fdx[:, 0].copy(), F2[:, 0].copy(), F2dx[:, :, 0].copy()
+
+    def unitary_and_derivatives(self, x):
+        Hs, _, p = self.stacks(x)
+        h = self._handle(p, self._hermitian(Hs))
+        d, N, a, e = self.ndim, self.ntimes, self.na, self.nerr
+        z = lambda *s: np.zeros(s, dtype=np.complex128, order="F")
+        U, U_dx, U_dx_add, U_derr = z(d, d), z(d, d, p, N), z(d, d, a), z(d, d, e)
+        U_derr_dx, U_derr_dx_add = z(d, d, p, N, e), z(d, d, a, e)
+        self.ctx.check(self.ctx.lib.rg_unitary_and_derivatives_from_hstack(h, _ptr(Hs), _ptr(U), _ptr(U_dx), _ptr(U_dx_add), _ptr(U_derr),
+                                                                         _ptr(U_derr_dx), _ptr(U_derr_dx_add)))
+        return U, U_dx, U_dx_add, U_derr, U_derr_dx, U_derr_dx_add
+
+    def close(self):
+        for h in self._handles.values():
+            self.ctx.lib.rg_problem_destroy(h)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            if self.ctx.handle:
+                self.close()
+        except Exception:
+            pass
+
+
+def is_descriptor_problem(problem):
+    """True when every callable of the problem is a declarative term list (device-evaluable)."""
+    from .types import FidelityRobustGRAPEProblem
+    up = problem.unitary_problem if isinstance(problem, FidelityRobustGRAPEProblem) else problem
+    ok = isinstance(up.H0, D.TermHamiltonian) and all(isinstance(s.Herror, D.TermErrorHamiltonian) for s in up.error_sources)
+    if isinstance(problem, FidelityRobustGRAPEProblem):
+        ok = ok and isinstance(problem.target_unitary, D.TermTarget)
+    return ok

@@ -194,6 +194,10 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     P.inv_eps2sq = 1.0 / (desc->eps2 * desc->eps2);              // (1/eps2^2) (:80)
     P.nx = P.p * P.N + P.a;
     P.hermitian = desc->hermitian;
+    P.hstack = nullptr; P.tstack = nullptr; P.nexp = 0;
+    pr->is_hstack = desc->hstack != 0;
+    if (pr->is_hstack && (d > 10 || desc->nterms != 0 || desc->ntarget_terms != 0))
+        { ctx->err = "H-stack problems: ndim <= 10, nterms = ntarget_terms = 0"; rg_problem_destroy(pr); return RG_ERR_UNSUPPORTED; }
 
     std::string why;
     std::vector<DevTerm> ht, tt;
@@ -246,6 +250,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         for (auto& t : ht)
             for (int f = 0; f < t.nf; ++f)
                 if (t.f[f].kind <= RG_F_EXPI && t.f[f].space == RG_S_ADD && t.f[f].index == j) dep = true;
+        if (pr->is_hstack) dep = true;          // opaque closures: every additional parameter may enter the Hamiltonian
         if (dep) {
             if (P.nvar >= RG_MAX_VARS) return fail(RG_ERR_UNSUPPORTED, "too many perturbation variables");
             P.add_var[j] = P.nvar;
@@ -287,7 +292,8 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     P.nent = (int)he.size(); P.ents = upload(pr, he); P.colptr = upload(pr, hc);
     P.ntt = (int)tt.size(); P.tterms = upload(pr, tt);
     P.ntent = (int)te.size(); P.tents = upload(pr, te); P.tcolptr = upload(pr, tc);
-    pr->has_target = (desc->ntarget_terms > 0 && desc->projector != nullptr);
+    pr->has_target = ((desc->ntarget_terms > 0 || pr->is_hstack) && desc->projector != nullptr);
+    P.nexp = 1 + 2 * P.nvar + P.e * (2 + P.nvar);
 
     std::vector<double> P0(d * d, 0.0), Pm(d * d, 0.0), PP(d * d, 0.0), PPt(d * d, 0.0);
     if (desc->projector) {
@@ -328,7 +334,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
         pr->diag_alg = diag ? 1 : 0;
     }
     // ---- upper-triangle plan for the thread-per-step kernel (Hermitian, d <= 5, few terms)
-    if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS) {
+    if (P.hermitian && d <= 7 && P.nterms <= RG_T_MAX_TERMS && !pr->is_hstack) {
         const int npos = d * (d + 1) / 2;
         std::vector<std::vector<std::pair<int, std::pair<double, double>>>> lists(npos);
         std::vector<double> colw((size_t)std::max(1, P.nterms) * d, 0.0);
@@ -392,7 +398,7 @@ extern "C" void rg_problem_destroy(rg_problem* pr) {
     if (!pr) return;
     cudaSetDevice(pr->ctx->device);
     for (void* p : pr->owned) cudaFree(p);
-    pr->big_termM.release(); pr->big_tgtM.release();
+    pr->big_termM.release(); pr->big_tgtM.release(); pr->dHs.release(); pr->dTs.release();
     DevBuf* bufs[] = {&pr->ws, &pr->Qb, &pr->Wlb, &pr->Cb, &pr->Wb, &pr->Gb, &pr->G1b, &pr->H1b, &pr->F, &pr->F2,
                       &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq, &pr->dM};
     for (DevBuf* b : bufs) b->release();
@@ -545,4 +551,41 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
 }
 
 #include "rg_api_analysis.inl"
+
+// ---- closure problems through host-evaluated Hamiltonian stacks (include/robustgrape_b200.h) ---------------------------------
+static int hstack_upload(rg_problem* pr, const double* Hstack, const double* Tstack) {
+    rg_ctx* ctx = pr->ctx;
+    if (!pr->is_hstack) RG_FAIL(ctx, RG_ERR_INVALID, "problem was not created as an H-stack problem (rg_problem_desc.hstack)");
+    if (!Hstack) RG_FAIL(ctx, RG_ERR_INVALID, "null H-stack");
+    CU(ctx, cudaSetDevice(ctx->device));
+    DevProblem& P = pr->dp;
+    const size_t DD = (size_t)P.d * P.d;
+    const size_t hb = DD * P.nexp * P.N * sizeof(cplx), tb = DD * (1 + P.a) * sizeof(cplx);
+    if (pr->dHs.ensure(hb) || pr->dTs.ensure(tb)) RG_FAIL(ctx, RG_ERR_NOMEM, "device allocation failed");
+    CU(ctx, cudaMemcpyAsync(pr->dHs.p, Hstack, hb, cudaMemcpyHostToDevice, ctx->stream));
+    P.hstack = pr->dHs.as<cplx>();
+    P.tstack = nullptr;
+    if (Tstack) {
+        CU(ctx, cudaMemcpyAsync(pr->dTs.p, Tstack, tb, cudaMemcpyHostToDevice, ctx->stream));
+        P.tstack = pr->dTs.as<cplx>();
+    }
+    return RG_OK;
+}
+extern "C" int rg_fidelity_and_derivatives_from_hstack(rg_problem* pr, const double* Hstack, const double* Tstack, double* F, double* F_dx,
+                                                       double* F_d2err, double* F_d2err_dx) {
+    if (!pr) return RG_ERR_INVALID;
+    if (!Tstack) RG_FAIL(pr->ctx, RG_ERR_INVALID, "null target stack");
+    int rc = hstack_upload(pr, Hstack, Tstack);
+    if (rc) return rc;
+    std::vector<double> x0((size_t)pr->dp.nx, 0.0);       // the kernels index X; its values are not used by H-stack problems
+    return rg_fidelity_and_derivatives_batch(pr, 1, x0.data(), F, F_dx, F_d2err, F_d2err_dx);
+}
+extern "C" int rg_unitary_and_derivatives_from_hstack(rg_problem* pr, const double* Hstack, double* U, double* U_dx, double* U_dx_add,
+                                                      double* U_derr, double* U_derr_dx, double* U_derr_dx_add) {
+    if (!pr) return RG_ERR_INVALID;
+    int rc = hstack_upload(pr, Hstack, nullptr);
+    if (rc) return rc;
+    std::vector<double> x0((size_t)pr->dp.nx, 0.0);
+    return rg_unitary_and_derivatives(pr, x0.data(), U, U_dx, U_dx_add, U_derr, U_derr_dx, U_derr_dx_add);
+}
 #include "rg_peer.inl"

@@ -41,6 +41,11 @@ struct DevProblem {
     int ntrig;           // trig slots: distinct arguments u = scale * v + offset of the COS/SIN/EXPI factors of H0 and error terms
     int trig_space[RG_MAX_TRIG], trig_index[RG_MAX_TRIG];
     double trig_scale[RG_MAX_TRIG], trig_offset[RG_MAX_TRIG];
+    // H-stack problems (closures evaluated on the host, src/Types.jl:13,35,55): per step the n_exp Hamiltonians whose exponentials
+    // the reference forms (src/UnitaryCalculations.jl:45-97), column-major d x d complex, order: H0(x) | H0(x + eps e_v) |
+    // H0(x + eps2 e_v) | H0 + Herr_e(eps) | H0 + Herr_e(eps2) | H0(x + eps2 e_v) + Herr_e(x + eps2 e_v, eps2) [e major]; and the
+    // target stack U0(x_add) | U0(x_add + eps e_j).  Null for descriptor problems.
+    const double2* hstack; const double2* tstack; int nexp;
     int mixed_zero;      // 1: no error term depends on a perturbation variable (the mixed slots of dt*H itself vanish)
     int nx;              // p*N + a
     int nstore;          // matrices stored per time step: 1 + nvar + e + nvar*e
@@ -187,6 +192,18 @@ __device__ inline void term_coef(const DevTerm& t, const EvalCtx& c, int pspace,
         P = cmul(P, v);
     }
     base = P; delta = Dl;
+}
+
+// column l of -i dt (Hs[obj] - Hs[ref]) (ref < 0: no subtraction) from the H-stack of step k of pulse b
+template <int D>
+__device__ __forceinline__ void hstack_col(const DevProblem& P, int b, int k, int obj, int ref, cplx* M, int l, bool zero = false) {
+    const cplx* base = P.hstack + (((size_t)b * P.N + k) * P.nexp) * (D * D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        cplx h = zero ? cmk(0.0, 0.0) : base[(size_t)obj * D * D + i + D * l];
+        if (ref >= 0 && !zero) h = csub(h, base[(size_t)ref * D * D + i + D * l]);
+        M[i + D * l] = cmk(h.y * P.dt, -h.x * P.dt);
+    }
 }
 
 // Taylor degree for ||A||_1 <= theta with remainder below 2^-53 (expm section).

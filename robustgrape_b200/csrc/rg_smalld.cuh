@@ -397,7 +397,8 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
         // ---- base matrix A = -i dt H0(x_k)
         fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
         __syncwarp(amask);
-        assemble_col<D>(sd.ents, sd.colptr, coef, mA, l, ghost);
+        if (P.hstack) hstack_col<D>(P, b, k, 0, -1, mA, l, ghost);
+        else assemble_col<D>(sd.ents, sd.colptr, coef, mA, l, ghost);
         double nrm = 0.0;
 #pragma unroll
         for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
@@ -431,7 +432,13 @@ k_steps(const DevProblem P, const double* __restrict__ X, int B, int L, int nc,
                 fill_coefs<D>(P, sd.terms, cf, VK_ERR, o - nv, P.eps, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
             }
             __syncwarp(amask);
-            assemble_col<D>(sd.ents, sd.colptr, cf, mD, l, ghost);
+            if (P.hstack) {
+                // host-evaluated closures: difference of the stacked Hamiltonians (variables at eps, then H0 + Herr_e(eps))
+                if (nfo == 0) hstack_col<D>(P, b, k, 0, -1, mD, l, true);
+                else hstack_col<D>(P, b, k, o < nv ? 1 + o : 1 + 2 * nv + (o - nv), 0, mD, l, ghost);
+            } else {
+                assemble_col<D>(sd.ents, sd.colptr, cf, mD, l, ghost);
+            }
             if (sq) {
 #pragma unroll
                 for (int i = 0; i < D; ++i) mD[i + D * l] = cscale(mD[i + D * l], sc);
@@ -591,7 +598,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
 
     fill_coefs<D>(P, sd.terms, coef, VK_BASE, 0, 0.0, RG_S_NONE, 0, 0.0, xk, xadd, k, l);
     __syncwarp(amask);
-    assemble_col<D>(sd.ents, sd.colptr, coef, mA, l);
+    if (P.hstack) hstack_col<D>(P, b, k, 0, -1, mA, l);
+    else assemble_col<D>(sd.ents, sd.colptr, coef, mA, l);
     double nrm = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) { const cplx a = mA[i + D * l]; nrm += sqrt(a.x * a.x + a.y * a.y); }
@@ -613,7 +621,8 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
     for (int e = 0; e < ne; ++e) {
         fill_coefs<D>(P, sd.terms, coef + 2 * nt, VK_ERR, e, P.eps2, RG_S_NONE, 0, 0.0, xk, xadd, k, l);   // beta
         __syncwarp(amask);
-        assemble_col<D>(sd.ents, sd.colptr, coef + 2 * nt, mBe, l);
+        if (P.hstack) hstack_col<D>(P, b, k, 1 + 2 * nv + ne + e, 0, mBe, l);                 // beta = H0 + Herr_e(eps2) - H0
+        else assemble_col<D>(sd.ents, sd.colptr, coef + 2 * nt, mBe, l);
         if (sq) {
 #pragma unroll
             for (int i = 0; i < D; ++i) mBe[i + D * l] = cscale(mBe[i + D * l], sc);
@@ -625,8 +634,17 @@ k_steps_so(const DevProblem P, const double* __restrict__ X, int B, cplx* __rest
             fill_coefs<D>(P, sd.terms, coef + nt, VK_DX, 0, 0.0, sp, ix, h2, xk, xadd, k, l);              // alpha
             fill_coefs<D>(P, sd.terms, coef + 3 * nt, VK_ERR_DX, e, P.eps2, sp, ix, h2, xk, xadd, k, l);   // gamma
             __syncwarp(amask);
-            assemble_col<D>(sd.ents, sd.colptr, coef + nt, mAl, l);
-            assemble_col<D>(sd.ents, sd.colptr, coef + 3 * nt, mGa, l);
+            if (P.hstack) {
+                // alpha = H0(x + eps2 e_v) - H0 ;  gamma = [H0(x+eps2 e_v) + Herr_e(x+eps2 e_v, eps2)] - H0(x+eps2 e_v) - beta
+                hstack_col<D>(P, b, k, 1 + nv + v, 0, mAl, l);
+                hstack_col<D>(P, b, k, 1 + 2 * nv + 2 * ne + e * nv + v, 1 + nv + v, mGa, l);
+                const double sc0 = sq ? 1.0 / sc : 1.0;              // mBe is already scaled
+#pragma unroll
+                for (int i = 0; i < D; ++i) mGa[i + D * l] = csub(mGa[i + D * l], cscale(mBe[i + D * l], sc0));
+            } else {
+                assemble_col<D>(sd.ents, sd.colptr, coef + nt, mAl, l);
+                assemble_col<D>(sd.ents, sd.colptr, coef + 3 * nt, mGa, l);
+            }
             if (sq) {
 #pragma unroll
                 for (int i = 0; i < D; ++i) { mAl[i + D * l] = cscale(mAl[i + D * l], sc); mGa[i + D * l] = cscale(mGa[i + D * l], sc); }
@@ -757,6 +775,10 @@ __device__ __forceinline__ double fid_algebra(const DevProblem& P, cplx* base, c
         }
         __syncwarp(amask);
         assemble_col<D>(P.tents, P.tcolptr, coef, mU0, l);
+        if (P.tstack) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) mU0[i + D * l] = P.tstack[i + D * l];
+        }
     }
     const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
     gmm<D, OPC, OPN>(mM, mU0, mU, l, amask);              // M = U0^dag U   (or U0^dag E)
@@ -805,6 +827,11 @@ __device__ __forceinline__ double fid_algebra(const DevProblem& P, cplx* base, c
         }
         __syncwarp(amask);
         assemble_col<D>(P.tents, P.tcolptr, coef, mV, l);
+        if (P.tstack) {                                       // (U0(x_add + eps e_j) - U0(x_add)) / eps  (:35-40)
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                mV[i + D * l] = cscale(csub(P.tstack[(size_t)(1 + j) * D * D + i + D * l], P.tstack[i + D * l]), P.inv_eps);
+        }
         gmm<D, OPC, OPN>(mW, mV, mU, l, amask);           // S1 = V^dag U
         const cplx t3 = gtrace2<D, OPN, OPN>(cPP, mW, scratch, l, amask);      // tr(PP V^dag U)
         gmm<D, OPN, OPN>(T4, mW, T2, l, amask);           // S1 P M^dag

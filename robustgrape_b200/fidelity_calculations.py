@@ -10,14 +10,17 @@ import time
 
 import numpy as np
 
-from ._lib import _ptr
+from ._lib import HStackProblem, _ptr
 from .unitary_calculations import device_problem
 
 
 def calculate_fidelity_and_derivatives(fidelity_problem, x, ctx=None):
     """reference src/FidelityCalculations.jl:19-119 -> (F, F_dx_tot, F_d2err, F_d2err_dx_tot)."""
     x = np.asarray(x, dtype=np.float64)
-    F, Fdx, F2, F2dx = device_problem(fidelity_problem, ctx).fidelity_and_derivatives_batch(x[:, None])
+    dp = device_problem(fidelity_problem, ctx)
+    if isinstance(dp, HStackProblem):                       # closure problem: host-evaluated Hamiltonian stack
+        return dp.fidelity_and_derivatives(x)
+    F, Fdx, F2, F2dx = dp.fidelity_and_derivatives_batch(x[:, None])
     return float(F[0]), Fdx[:, 0].copy(), F2[:, 0].copy(), F2dx[:, :, 0].copy()
 
 

@@ -3,14 +3,29 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import Problem, _ptr
+from ._lib import HStackProblem, Problem, _ptr, is_descriptor_problem
 
 
-def device_problem(problem, ctx=None) -> Problem:
-    """Device-resident twin of a problem struct, cached on the struct itself."""
+def _fingerprint(problem):
+    """Fields the device twin depends on: a changed struct gets a new twin (the reference re-reads its fields on every call)."""
+    up = getattr(problem, "unitary_problem", problem)
+    proj = getattr(problem, "projector", None)
+    return (id(up.H0), tuple(id(s.Herror) for s in up.error_sources), id(getattr(problem, "target_unitary", None)),
+            float(up.t0), int(up.ntimes), int(up.ndim), int(up.nb_additional_param), float(up.eps), float(up.eps2),
+            None if proj is None else np.asarray(proj, dtype=np.float64).tobytes())
+
+
+def device_problem(problem, ctx=None):
+    """Device-resident twin of a problem struct, cached on the struct itself and rebuilt when a field changed.  Descriptor
+    problems evaluate their Hamiltonians on the device (Problem); closure problems go through host-evaluated stacks (HStackProblem)."""
     dp = getattr(problem, "_rg_device_problem", None)
-    if dp is None or (ctx is not None and dp.ctx is not ctx):
-        dp = Problem(problem, ctx)
+    fpn = _fingerprint(problem)
+    if dp is None or (ctx is not None and dp.ctx is not ctx) or getattr(problem, "_rg_device_fingerprint", None) != fpn:
+        dp = Problem(problem, ctx) if is_descriptor_problem(problem) else HStackProblem(problem, ctx)
+        try:
+            object.__setattr__(problem, "_rg_device_fingerprint", fpn)
+        except Exception:
+            pass
         try:
             object.__setattr__(problem, "_rg_device_problem", dp)
         except Exception:
@@ -31,6 +46,8 @@ def calculate_unitary_and_derivatives(problem, x, ctx=None):
     (the reference's containers have abstract eltype `Complex`; values are the same)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     dp = device_problem(problem, ctx)
+    if isinstance(dp, HStackProblem):
+        return dp.unitary_and_derivatives(x)
     h, p = dp.handle_for(len(x))
     d, N, a, e = problem.ndim, problem.ntimes, problem.nb_additional_param, len(problem.error_sources)
     z = lambda *s: np.zeros(s, dtype=np.complex128, order="F")

@@ -581,3 +581,30 @@ def test_dense_path_config5_shape(gpu_ctx):
     c2 = 1 - F + sum(coeff[e] * F2[e] ** 2 for e in range(4))
     g2 = -Fdx + sum(2 * coeff[e] * F2[e][None, :] * F2dx[:, e, :] for e in range(4))
     assert np.abs(c - c2).max() < 1e-13 and np.abs(g - g2).max() < 1e-12
+
+
+@pytest.mark.parametrize("errors,N", [((), 30), (("amp",), 25), (("amp", "freq"), 18)])
+def test_closure_problems_through_the_hstack_entry_points(gpu_ctx, errors, N):
+    """the reference's own call style -- plain closures calling the literal RydbergTools builders
+    (examples/time_optimal_cz.jl:15-16,60-61; test/runtests.jl:474-476) -- runs through rg_*_from_hstack.  The host evaluates
+    the closures, the device does the rest; compared with the literal restatement at its finite-difference noise floor."""
+    from cases import cz_problem_closures
+    fp = cz_problem_closures(N, 7.613 * N / 300, errors)
+    x = random_pulse(fp, 1, 60 + N)
+    got = rg.calculate_fidelity_and_derivatives(fp, x)
+    ref = ro.calculate_fidelity_and_derivatives(fp, x)
+    assert abs(got[0] - ref[0]) < 1e-12
+    for k, g, r, tol in zip(NAMES[1:], got[1:], ref[1:], (2e-5, 2e-5, 2e-4)):
+        assert relmax(g, r) < tol, (k, relmax(g, r))
+    # the same problem written with descriptors agrees with the closure version within that noise floor
+    desc = rg.calculate_fidelity_and_derivatives(cz_problem(N, 7.613 * N / 300, errors), x)
+    assert abs(got[0] - desc[0]) < 1e-13
+    for k, g, r, tol in zip(NAMES[1:], got[1:], desc[1:], (2e-5, 2e-5, 2e-4)):
+        assert relmax(g, r) < tol, (k, relmax(g, r))
+    U = rg.calculate_unitary_and_derivatives(fp.unitary_problem, x)
+    Ur = ro.calculate_unitary_and_derivatives(fp.unitary_problem, x)
+    assert np.abs(U[0] - Ur[0]).max() < 1e-12
+    assert np.abs(U[1] - Ur[1]).max() < 2e-5 * np.abs(Ur[1]).max()
+    if errors:
+        assert np.abs(U[3] - Ur[3]).max() < 2e-5 * np.abs(Ur[3]).max()
+        assert np.abs(U[4] - Ur[4]).max() < 2e-4 * np.abs(Ur[4]).max()

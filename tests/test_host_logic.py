@@ -83,9 +83,34 @@ def test_library_exports_every_declared_symbol(built_library):
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
 
 
-def test_closures_are_rejected_loudly():
+def test_closures_take_the_hstack_path_and_never_the_descriptor_path():
+    """Closures cannot be evaluated on the device: the descriptor Problem rejects them loudly, and device_problem routes them
+    to the host-evaluated H-stack entry points (rg_*_from_hstack) instead."""
     with pytest.raises(_lib.DescriptorError):
         _lib.Problem(cz_problem_closures(10, 1.0), ctx=object())
+    assert not _lib.is_descriptor_problem(cz_problem_closures(10, 1.0))
+    assert _lib.is_descriptor_problem(cz_problem(10, 1.0, ("amp",)))
+
+
+def test_hstack_layout_matches_reference_perturbation_pattern():
+    """Order and arithmetic of the stacked Hamiltonians (src/UnitaryCalculations.jl:45-97)."""
+    from robustgrape_b200 import rydberg_tools as rt
+    fp = cz_problem_closures(4, 1.0, ("amp", "freq"))
+    hp = _lib.HStackProblem.__new__(_lib.HStackProblem)
+    hp.up, hp.fp = fp.unitary_problem, fp
+    hp.ndim, hp.ntimes, hp.na, hp.nerr = 5, 4, 1, 2
+    x = np.array([0.3, 0.7, 1.1, 1.9, 0.4])
+    Hs, Ts, p = hp.stacks(x)
+    assert p == 1 and Hs.shape == (5, 5, 1 + 4 + 2 * 4, 4) and Ts.shape == (5, 5, 2)
+    k = 2
+    assert np.array_equal(Hs[:, :, 0, k], rt.rydberg_hamiltonian_symmetric_blockaded(x[k], 0, 0))
+    assert np.array_equal(Hs[:, :, 1, k], rt.rydberg_hamiltonian_symmetric_blockaded(x[k] + 1e-8, 0, 0))
+    assert np.array_equal(Hs[:, :, 3, k], rt.rydberg_hamiltonian_symmetric_blockaded(x[k] + 1e-4, 0, 0))
+    assert np.array_equal(Hs[:, :, 2, k], Hs[:, :, 0, k])          # the additional parameter does not enter this Hamiltonian
+    H0 = rt.rydberg_hamiltonian_symmetric_blockaded(x[k], 0, 0)
+    assert np.array_equal(Hs[:, :, 5, k], H0 + (rt.rydberg_hamiltonian_symmetric_blockaded(x[k], 1e-8, 0) - H0))
+    assert np.array_equal(Hs[:, :, 8, k], H0 + (rt.rydberg_hamiltonian_symmetric_blockaded(x[k], 0, 1e-4) - H0))
+    assert np.array_equal(Ts[:, :, 1], rt.cz_with_1q_phase_symmetric(x[4] + 1e-8))
 
 
 def test_no_cpu_fallback(built_library):
