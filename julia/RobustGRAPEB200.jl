@@ -4,6 +4,13 @@
 # image (no network), so this file has never been loaded.  The Python mirror (robustgrape_b200/*.py) binds the
 # identical C ABI through ctypes and is what the test-suite exercises.  See INTEGRATION.md.
 #
+# All seven reference functions of the hot path are bound:
+#   calculate_unitary_and_derivatives, calculate_interaction_error_operators            (src/UnitaryCalculations.jl:20,180)
+#   calculate_fidelity_and_derivatives, calculate_fidelity_response, calculate_fidelity_response_fft,
+#   calculate_expectation_values, optimize_fidelity_and_error_sources                   (src/FidelityCalculations.jl:19,161,246,306,368)
+# Problems whose H0 / Herror / target_unitary are descriptors (below) are evaluated entirely on the GPU; problems with
+# ordinary Julia closures are evaluated on the host into an H-stack and go through rg_*_from_hstack (any closure works).
+#
 # Usage (drop-in for the hot path):
 #     using RobustGRAPE, RobustGRAPEB200
 #     H0   = RobustGRAPEB200.rydberg_h0(:symmetric_blockaded)           # instead of a closure
@@ -47,6 +54,7 @@ struct CProblemDesc       # rg_problem_desc
     projector::Ptr{Float64}
     ntable_cols::Int32; table::Ptr{Float64}
     hermitian::Int32
+    hstack::Int32
 end
 
 # ---- declarative operators ---------------------------------------------------------------------------
@@ -173,24 +181,49 @@ function _cterms(terms::Vector{Term}, owner::Int32, keep::Vector{Any})
     return out
 end
 
-"Build the device-resident twin of a FidelityRobustGRAPEProblem whose closures are descriptors."
-function DeviceProblem(fp::FidelityRobustGRAPEProblem, nparam::Int; ctx::Context=default_context())
-    up = fp.unitary_problem
-    up.H0 isa TermHamiltonian || error("H0 must be a RobustGRAPEB200.TermHamiltonian: the GPU cannot call a Julia closure")
-    keep = Any[]
-    terms = _cterms(up.H0.terms, RG_OWNER_H0, keep)
-    for (e, src) in enumerate(up.error_sources)
-        src.Herror isa TermErrorHamiltonian || error("error source $e must be a TermErrorHamiltonian")
-        append!(terms, _cterms(src.Herror.terms, Int32(e - 1), keep))
+_unitary(p::UnitaryRobustGRAPEProblem) = p
+_unitary(p::FidelityRobustGRAPEProblem) = p.unitary_problem
+is_descriptor_problem(p::UnitaryRobustGRAPEProblem) =
+    p.H0 isa TermHamiltonian && all(s.Herror isa TermErrorHamiltonian for s in p.error_sources)
+is_descriptor_problem(p::FidelityRobustGRAPEProblem) = is_descriptor_problem(p.unitary_problem) && p.target_unitary isa TermTarget
+
+"Hermitian for real variables?  Checked numerically at a few random points (non-Hermitian H0, e.g. -i gamma/2 decay, is legal:
+the reference uses inv, src/UnitaryCalculations.jl:47)."
+function _is_hermitian(up::UnitaryRobustGRAPEProblem, nparam::Int)
+    for _ in 1:3
+        x = randn(max(nparam, 1)); xa = randn(max(up.nb_additional_param, 1))
+        M = up.H0(1, x, xa)
+        maximum(abs.(M - M')) <= 1e-13 * max(1.0, maximum(abs.(M))) || return false
+        for s in up.error_sources
+            E = s.Herror(1, x, xa, randn())
+            maximum(abs.(E - E')) <= 1e-13 * max(1.0, maximum(abs.(E))) || return false
+        end
     end
-    fp.target_unitary isa TermTarget || error("target_unitary must be a TermTarget")
-    tterms = _cterms(fp.target_unitary.terms, RG_OWNER_TARGET, keep)
-    proj = Matrix{Float64}(fp.projector)
+    return true
+end
+
+"Build the device-resident twin of a problem.  Descriptor problems carry their term lists; closure problems are created as
+H-stack problems (`hstack = 1`, no terms) and are fed host-evaluated Hamiltonians per call."
+function DeviceProblem(prob, nparam::Int; ctx::Context=default_context(), hermitian::Union{Nothing,Bool}=nothing)
+    up = _unitary(prob)
+    keep = Any[]
+    terms = CTerm[]; tterms = CTerm[]
+    descr = is_descriptor_problem(prob)
+    if descr
+        terms = _cterms(up.H0.terms, RG_OWNER_H0, keep)
+        for (e, src) in enumerate(up.error_sources)
+            append!(terms, _cterms(src.Herror.terms, Int32(e - 1), keep))
+        end
+        prob isa FidelityRobustGRAPEProblem && (tterms = _cterms(prob.target_unitary.terms, RG_OWNER_TARGET, keep))
+    end
+    proj = prob isa FidelityRobustGRAPEProblem ? Matrix{Float64}(prob.projector) : Float64[]
+    herm = hermitian === nothing ? _is_hermitian(up, nparam) : hermitian
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep terms tterms proj begin
         desc = Ref(CProblemDesc(up.ndim, up.ntimes, nparam, up.nb_additional_param, length(up.error_sources),
-                                up.t0, up.ϵ, up.ϵ2, length(terms), pointer(terms), length(tterms), pointer(tterms),
-                                pointer(proj), 0, C_NULL, 1))
+                                up.t0, up.ϵ, up.ϵ2, length(terms), isempty(terms) ? C_NULL : pointer(terms),
+                                length(tterms), isempty(tterms) ? C_NULL : pointer(tterms),
+                                isempty(proj) ? C_NULL : pointer(proj), 0, C_NULL, herm ? 1 : 0, descr ? 0 : 1))
         check(ctx, ccall((:rg_problem_create, LIB), Cint, (Ptr{Cvoid}, Ref{CProblemDesc}, Ref{Ptr{Cvoid}}), ctx.handle, desc, h))
     end
     p = DeviceProblem(ctx, h[], length(up.error_sources), up.ntimes, up.nb_additional_param)
@@ -198,19 +231,149 @@ function DeviceProblem(fp::FidelityRobustGRAPEProblem, nparam::Int; ctx::Context
     return p
 end
 
+"Host evaluation of closures into the stacks rg_*_from_hstack take (include/robustgrape_b200.h), with the reference's
+perturbation arithmetic (src/UnitaryCalculations.jl:50-55,58-63,76-84,88-96; src/FidelityCalculations.jl:32-40)."
+function hstacks(prob, x::Vector{Float64})
+    up = _unitary(prob)
+    N, d, a, ne = up.ntimes, up.ndim, up.nb_additional_param, length(up.error_sources)
+    nmain = length(x) - a
+    @assert mod(nmain, N) == 0 "Control parameter size must be a multiple of time steps"
+    p = nmain ÷ N; nvar = p + a
+    nexp = 1 + 2nvar + ne * (2 + nvar)
+    xm = reshape(x[1:nmain], p, N); xa = x[nmain+1:end]
+    Hs = zeros(ComplexF64, d, d, nexp, N)
+    function pert(k, v, h)
+        xk = xm[:, k]; xad = copy(xa)
+        v <= p ? (xk[v] += h) : (xad[v-p] += h)
+        return xk, xad
+    end
+    for k in 1:N
+        xk = xm[:, k]
+        base = ComplexF64.(up.H0(k, xk, xa))
+        Hs[:, :, 1, k] = base
+        for v in 1:nvar
+            Hs[:, :, 1+v, k] = up.H0(k, pert(k, v, up.ϵ)...)
+            Hs[:, :, 1+nvar+v, k] = up.H0(k, pert(k, v, up.ϵ2)...)
+        end
+        for (e, src) in enumerate(up.error_sources)
+            Hs[:, :, 1+2nvar+e, k] = base + src.Herror(k, xk, xa, up.ϵ)
+            Hs[:, :, 1+2nvar+ne+e, k] = base + src.Herror(k, xk, xa, up.ϵ2)
+            for v in 1:nvar
+                xk2, xa2 = pert(k, v, up.ϵ2)
+                Hs[:, :, 1+2nvar+2ne+(e-1)*nvar+v, k] = up.H0(k, xk2, xa2) + src.Herror(k, xk2, xa2, up.ϵ2)
+            end
+        end
+    end
+    Ts = zeros(ComplexF64, d, d, 1 + a)
+    if prob isa FidelityRobustGRAPEProblem
+        Ts[:, :, 1] = prob.target_unitary(xa)
+        for j in 1:a
+            xa2 = copy(xa); xa2[j] += up.ϵ
+            Ts[:, :, 1+j] = prob.target_unitary(xa2)
+        end
+    end
+    herm = maximum(abs.(Hs .- conj.(permutedims(Hs, (2, 1, 3, 4))))) <= 1e-13 * max(1.0, maximum(abs.(Hs)))
+    return Hs, Ts, p, herm
+end
+
 const _CACHE = IdDict{Any,DeviceProblem}()
-function device_problem(fp, x)
-    get!(_CACHE, fp) do
-        nparam = (length(x) - fp.unitary_problem.nb_additional_param) ÷ fp.unitary_problem.ntimes
-        DeviceProblem(fp, nparam)
+function device_problem(prob, x)
+    get!(_CACHE, prob) do
+        up = _unitary(prob)
+        DeviceProblem(prob, (length(x) - up.nb_additional_param) ÷ up.ntimes)
     end
 end
 
 # ---- the hot path ----------------------------------------------------------------------------------
 "Replaces RobustGRAPE.calculate_fidelity_and_derivatives (src/FidelityCalculations.jl:19-119)."
 function calculate_fidelity_and_derivatives(fp::FidelityRobustGRAPEProblem, x::Vector{Float64})
+    if !is_descriptor_problem(fp)                       # ordinary closures: host-evaluated H-stack
+        Hs, Ts, p, herm = hstacks(fp, x)
+        dp = DeviceProblem(fp, p; hermitian=herm)
+        nx = length(x); ne = dp.nerr
+        F = zeros(1); Fdx = zeros(nx, 1); F2 = zeros(ne, 1); F2dx = zeros(nx, ne, 1)
+        GC.@preserve Hs Ts F Fdx F2 F2dx begin
+            check(dp.ctx, ccall((:rg_fidelity_and_derivatives_from_hstack, LIB), Cint,
+                                (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                dp.handle, Hs, Ts, F, Fdx, F2, F2dx))
+        end
+        return F[1], Fdx[:, 1], F2[:, 1], F2dx[:, :, 1]
+    end
     F, Fdx, F2, F2dx = calculate_fidelity_and_derivatives_batch(fp, reshape(x, :, 1))
     return F[1], Fdx[:, 1], F2[:, 1], F2dx[:, :, 1]
+end
+
+"Replaces RobustGRAPE.calculate_unitary_and_derivatives (src/UnitaryCalculations.jl:20-155); returns concrete ComplexF64 arrays
+of the reference's shapes (the reference's containers have abstract eltype `Complex`, src/UnitaryCalculations.jl:106-110)."
+function calculate_unitary_and_derivatives(up::UnitaryRobustGRAPEProblem, x::Vector{Float64})
+    N, d, a, e = up.ntimes, up.ndim, up.nb_additional_param, length(up.error_sources)
+    @assert mod(length(x) - a, N) == 0 "Control parameter size must be a multiple of time steps"
+    p = (length(x) - a) ÷ N
+    U = zeros(ComplexF64, d, d); U_dx = zeros(ComplexF64, d, d, p, N); U_dx_add = zeros(ComplexF64, d, d, a)
+    U_derr = zeros(ComplexF64, d, d, e); U_derr_dx = zeros(ComplexF64, d, d, p, N, e); U_derr_dx_add = zeros(ComplexF64, d, d, a, e)
+    T = Ptr{ComplexF64}
+    if is_descriptor_problem(up)
+        dp = device_problem(up, x)
+        GC.@preserve x U U_dx U_dx_add U_derr U_derr_dx U_derr_dx_add begin
+            check(dp.ctx, ccall((:rg_unitary_and_derivatives, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, T, T, T, T, T, T),
+                                dp.handle, x, U, U_dx, U_dx_add, U_derr, U_derr_dx, U_derr_dx_add))
+        end
+    else
+        Hs, _, _, herm = hstacks(up, x)
+        dp = DeviceProblem(up, p; hermitian=herm)
+        GC.@preserve Hs U U_dx U_dx_add U_derr U_derr_dx U_derr_dx_add begin
+            check(dp.ctx, ccall((:rg_unitary_and_derivatives_from_hstack, LIB), Cint, (Ptr{Cvoid}, T, T, T, T, T, T, T),
+                                dp.handle, Hs, U, U_dx, U_dx_add, U_derr, U_derr_dx, U_derr_dx_add))
+        end
+    end
+    return U, U_dx, U_dx_add, U_derr, U_derr_dx, U_derr_dx_add
+end
+
+"Replaces RobustGRAPE.calculate_interaction_error_operators (src/UnitaryCalculations.jl:180-204): (ndim, ndim, ntimes, nerr)."
+function calculate_interaction_error_operators(up::UnitaryRobustGRAPEProblem, x::Vector{Float64})
+    dp = device_problem(up, x)
+    O = zeros(ComplexF64, up.ndim, up.ndim, up.ntimes, length(up.error_sources))
+    GC.@preserve x O begin
+        check(dp.ctx, ccall((:rg_interaction_error_operators, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{ComplexF64}), dp.handle, x, O))
+    end
+    return O
+end
+
+"Replaces RobustGRAPE.calculate_fidelity_response (src/FidelityCalculations.jl:246-280): (nfreq, nerr).  `first`/`count`
+(0-based first row, number of rows) select a shard of the frequency grid for multi-GPU use."
+function calculate_fidelity_response(fp::FidelityRobustGRAPEProblem, x::Vector{Float64}, normalized_frequencies::Vector{Float64};
+                                     first::Int=0, count::Int=length(normalized_frequencies) - first)
+    dp = device_problem(fp, x)
+    R = zeros(count, dp.nerr)
+    GC.@preserve x normalized_frequencies R begin
+        check(dp.ctx, ccall((:rg_fidelity_response, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32, Ptr{Float64}),
+                            dp.handle, x, normalized_frequencies, length(normalized_frequencies), first, count, R))
+    end
+    return R
+end
+
+"Replaces RobustGRAPE.calculate_fidelity_response_fft (src/FidelityCalculations.jl:306-343): (response (N*os, nerr), frequencies)."
+function calculate_fidelity_response_fft(fp::FidelityRobustGRAPEProblem, x::Vector{Float64}; oversampling::Int=1)
+    @assert oversampling >= 1
+    dp = device_problem(fp, x)
+    n = dp.ntimes * oversampling
+    R = zeros(n, dp.nerr); fr = zeros(n)
+    GC.@preserve x R fr begin
+        check(dp.ctx, ccall((:rg_fidelity_response_fft, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}),
+                            dp.handle, x, oversampling, R, fr))
+    end
+    return R, fr
+end
+
+"Replaces RobustGRAPE.calculate_expectation_values (src/FidelityCalculations.jl:368-390): (ntimes, nerr)."
+function calculate_expectation_values(fp::FidelityRobustGRAPEProblem, x::Vector{Float64})
+    dp = device_problem(fp, x)
+    out = zeros(dp.ntimes, dp.nerr)
+    GC.@preserve x out begin
+        check(dp.ctx, ccall((:rg_expectation_values, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), dp.handle, x, out))
+    end
+    return out
 end
 
 "Batched variant: X is (nx, B), one pulse per column."

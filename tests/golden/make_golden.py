@@ -22,6 +22,11 @@ from cases import golden_cases  # noqa: E402
 from oracle import exact_oracle as eo, reference_oracle as ro  # noqa: E402
 
 if __name__ == "__main__":
+    if "--export-inputs" in sys.argv:          # inputs of every case as CSV for tests/golden/make_golden.jl (the Julia reference run)
+        for name in golden_cases():
+            z = np.load(Path(__file__).parent / f"{name}.npz")
+            np.savetxt(Path(__file__).parent / f"{name}_x.csv", z["x"][None, :], delimiter=",", fmt="%.17g")
+        sys.exit(0)
     only = set(sys.argv[1:])
     for name, (fp, x) in golden_cases().items():
         if only and name not in only:
