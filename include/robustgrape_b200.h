@@ -125,6 +125,29 @@ int rg_fidelity_and_derivatives_batch_dev(rg_problem* prob, int32_t B, const dou
 int rg_cost_and_grad_batch_dev(rg_problem* prob, int32_t B, const double* dX, const double* err_coeff,
                                double* dcost, double* dgrad);
 
+/* --- the optimiser loop on the device --------------------------------------------------------------
+ * Regularisation terms of calculate_common! (src/FidelityCalculations.jl:186-195) as an enumerated device epilogue, one kind per
+ * control row:  RG_REG_PLAIN = regularization_cost (src/Regularization.jl:26-47), RG_REG_PHASE = regularization_cost_phase
+ * (:111-115), RG_REG_SIN2 = the sin^2-of-differences form the reference's tests use (test/runtests.jl:9-45).
+ *   cost += sum_np c1[np] reg1 + c2[np] reg2 ;  grad[main parameters] += c1[np] jac1 + c2[np] jac2.
+ * reg_kind / reg_c1 / reg_c2 have nparam entries (host); reg_kind may be NULL (no regularisation).                            */
+enum { RG_REG_NONE = 0, RG_REG_PLAIN = 1, RG_REG_PHASE = 2, RG_REG_SIN2 = 3 };
+int rg_cost_and_grad_batch_reg(rg_problem* prob, int32_t B, const double* X, const double* err_coeff, const int32_t* reg_kind,
+                               const double* reg_c1, const double* reg_c2, double* cost, double* grad);
+int rg_cost_and_grad_batch_reg_dev(rg_problem* prob, int32_t B, const double* dX, const double* err_coeff, const int32_t* reg_kind,
+                                   const double* reg_c1, const double* reg_c2, double* dcost, double* dgrad);
+/* Batched L-BFGS, one independent optimiser per pulse, in place of Optim.optimize(f, g!, x0; method = LBFGS(), iterations, g_tol)
+ * (src/FidelityCalculations.jl:199-217) for multi-start runs: the iterates, gradients and curvature history stay in HBM and only a
+ * 12-byte progress record crosses PCIe per line-search round.  X (nx, B) is updated in place (host or device buffer); cost (B);
+ * iters_out (B, host, may be NULL); info_out (3 ints, host, may be NULL): evaluations, iterations, line-search failures.
+ * history <= 32 curvature pairs; stops when every pulse has ||grad||_inf <= g_tol or after `iterations`.                    */
+int rg_lbfgs_batch(rg_problem* prob, int32_t B, double* X, const double* err_coeff, const int32_t* reg_kind, const double* reg_c1,
+                   const double* reg_c2, int32_t history, int32_t iterations, double g_tol, double* cost, int32_t* iters_out,
+                   int32_t* info_out);
+int rg_lbfgs_batch_dev(rg_problem* prob, int32_t B, double* dX, const double* err_coeff, const int32_t* reg_kind, const double* reg_c1,
+                       const double* reg_c2, int32_t history, int32_t iterations, double g_tol, double* dcost, int32_t* iters_out,
+                       int32_t* info_out);
+
 /* calculate_unitary_and_derivatives (src/UnitaryCalculations.jl:20-155), one pulse, materialised:
  * U (d,d), U_dx (d,d,p,N), U_dx_add (d,d,a), U_derr (d,d,e), U_derr_dx (d,d,p,N,e),
  * U_derr_dx_add (d,d,a,e); complex interleaved.  Output pointers may be NULL.                    */

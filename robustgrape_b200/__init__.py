@@ -9,7 +9,7 @@ from .unitary_calculations import calculate_unitary_and_derivatives, calculate_i
 from .fidelity_calculations import (calculate_fidelity_and_derivatives, optimize_fidelity_and_error_sources,
                                     calculate_fidelity_response, calculate_fidelity_response_fft,
                                     calculate_expectation_values, calculate_fidelity_and_derivatives_batch,
-                                    cost_and_gradient_batch)
+                                    cost_and_gradient_batch, optimize_batch_device)
 from .regularization import regularization_cost, regularization_cost_phase
 
 RydbergTools = rydberg_tools

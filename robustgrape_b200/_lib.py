@@ -67,6 +67,10 @@ SIGNATURES = {
     "rg_cost_and_grad_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
     "rg_fidelity_and_derivatives_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "rg_cost_and_grad_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp]),
+    "rg_cost_and_grad_batch_reg": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_cost_and_grad_batch_reg_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rg_lbfgs_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, _vp, _vp, _vp]),
+    "rg_lbfgs_batch_dev": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, _vp, _vp, _vp]),
     "rg_unitary_and_derivatives": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_fidelity_and_derivatives_from_hstack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rg_unitary_and_derivatives_from_hstack": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -357,6 +361,57 @@ class Problem:
         grad = np.zeros((nx, B), order="F")
         self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch(h, B, _ptr(X), _ptr(coeff) if self.nerr else None, _ptr(cost), _ptr(grad)))
         return cost, grad
+
+    def _reg_arrays(self, p, reg):
+        """reg: None or a list of (kind, c1, c2) per control row -> ctypes-ready arrays (kept alive on self)."""
+        if not reg:
+            return None, None, None
+        if len(reg) != p:
+            raise AssertionError("one regularisation entry per control parameter")
+        k = np.array([r[0] for r in reg], dtype=np.int32)
+        c1 = np.array([r[1] for r in reg], dtype=np.float64)
+        c2 = np.array([r[2] for r in reg], dtype=np.float64)
+        self._keep_reg = (k, c1, c2)
+        return k, c1, c2
+
+    def cost_and_grad_batch_reg(self, X, error_source_coeff=(), reg=None):
+        """calculate_common! including the enumerated regularisation terms, all on the device."""
+        X, nx, B = self._batch_in(X)
+        h, p = self.handle_for(nx)
+        coeff = np.asarray(error_source_coeff, dtype=np.float64)
+        k, c1, c2 = self._reg_arrays(p, reg)
+        cost = np.zeros(B)
+        grad = np.zeros((nx, B), order="F")
+        self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch_reg(h, B, _ptr(X), _ptr(coeff) if self.nerr else None, _ptr(k), _ptr(c1), _ptr(c2),
+                                                             _ptr(cost), _ptr(grad)))
+        return cost, grad
+
+    def lbfgs_batch(self, X0, error_source_coeff=(), reg=None, history=10, iterations=100, g_tol=1e-8):
+        """Batched device L-BFGS from the columns of X0 (nx, B).  Returns (X, cost, iterations per pulse, info dict)."""
+        X, nx, B = self._batch_in(X0)
+        X = X.copy(order="F")
+        h, p = self.handle_for(nx)
+        coeff = np.asarray(error_source_coeff, dtype=np.float64)
+        if len(coeff) != self.nerr:
+            raise AssertionError("error_source_coeff must have one entry per error source")
+        k, c1, c2 = self._reg_arrays(p, reg)
+        cost = np.zeros(B)
+        iters = np.zeros(B, dtype=np.int32)
+        info = np.zeros(3, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rg_lbfgs_batch(h, B, _ptr(X), _ptr(coeff) if self.nerr else None, _ptr(k), _ptr(c1), _ptr(c2),
+                                                 int(history), int(iterations), float(g_tol), _ptr(cost), _ptr(iters), _ptr(info)))
+        return X, cost, iters, {"evaluations": int(info[0]), "iterations": int(info[1]), "line_search_failures": int(info[2])}
+
+    def lbfgs_batch_dev(self, B, nx, dX_ptr, error_source_coeff, dcost_ptr, reg=None, history=10, iterations=100, g_tol=1e-8):
+        """Device-pointer variant of lbfgs_batch: X (nx, B) is optimised in place in HBM.  Returns (iters, info)."""
+        h, p = self.handle_for(nx)
+        coeff = np.asarray(error_source_coeff, dtype=np.float64)
+        k, c1, c2 = self._reg_arrays(p, reg)
+        iters = np.zeros(B, dtype=np.int32)
+        info = np.zeros(3, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.rg_lbfgs_batch_dev(h, B, _vp(dX_ptr), _ptr(coeff) if self.nerr else None, _ptr(k), _ptr(c1), _ptr(c2),
+                                                     int(history), int(iterations), float(g_tol), _vp(dcost_ptr), _ptr(iters), _ptr(info)))
+        return iters, {"evaluations": int(info[0]), "iterations": int(info[1]), "line_search_failures": int(info[2])}
 
     def cost_and_grad_batch_dev(self, B, nx, dX_ptr, error_source_coeff, dcost_ptr, dgrad_ptr):
         """Device-pointer variant (integers from e.g. torch.Tensor.data_ptr()); asynchronous."""

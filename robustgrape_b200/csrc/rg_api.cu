@@ -398,7 +398,7 @@ extern "C" void rg_problem_destroy(rg_problem* pr) {
     if (!pr) return;
     cudaSetDevice(pr->ctx->device);
     for (void* p : pr->owned) cudaFree(p);
-    pr->big_termM.release(); pr->big_tgtM.release(); pr->dHs.release(); pr->dTs.release();
+    pr->big_termM.release(); pr->big_tgtM.release(); pr->dHs.release(); pr->dTs.release(); pr->regbuf.release(); pr->lbfgs.release(); pr->dXopt.release();
     DevBuf* bufs[] = {&pr->ws, &pr->Qb, &pr->Wlb, &pr->Cb, &pr->Wb, &pr->Gb, &pr->G1b, &pr->H1b, &pr->F, &pr->F2,
                       &pr->addT, &pr->addS, &pr->F2dx, &pr->Fdx, &pr->coeff, &pr->dX, &pr->dOut, &pr->dOut2, &pr->dO, &pr->dFreq, &pr->dM};
     for (DevBuf* b : bufs) b->release();
@@ -551,6 +551,7 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
 }
 
 #include "rg_api_analysis.inl"
+#include "rg_api_optim.inl"
 
 // ---- closure problems through host-evaluated Hamiltonian stacks (include/robustgrape_b200.h) ---------------------------------
 static int hstack_upload(rg_problem* pr, const double* Hstack, const double* Tstack) {

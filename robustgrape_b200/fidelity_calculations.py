@@ -35,11 +35,39 @@ def cost_and_gradient_batch(fidelity_problem, X, error_source_coeff=(), ctx=None
     return device_problem(fidelity_problem, ctx).cost_and_grad_batch(X, error_source_coeff)
 
 
+def optimize_batch_device(fidelity_problem, X0, error_source_coeff=(), regularization_functions=None, regularization_coeff1=None,
+                          regularization_coeff2=None, iterations=1000, g_tol=1e-8, history=10, ctx=None):
+    """Multi-start optimisation with the whole loop on the device: one L-BFGS per column of X0 (nx, B), cost =
+    calculate_common! (src/FidelityCalculations.jl:174-197) with enumerated regularisation (regularization.device_kinds).
+    Returns (X, cost, iterations per pulse, info)."""
+    from . import regularization as R
+    dp = device_problem(fidelity_problem, ctx)
+    reg = None
+    if regularization_functions:
+        kinds = R.device_kinds(regularization_functions)
+        if kinds is None:
+            raise TypeError("device optimisation needs enumerated regularisation functions (robustgrape_b200.regularization); "
+                            "arbitrary callables run through optimize_fidelity_and_error_sources")
+        reg = list(zip(kinds, regularization_coeff1, regularization_coeff2))
+    return dp.lbfgs_batch(X0, error_source_coeff, reg, history, iterations, g_tol)
+
+
 def optimize_fidelity_and_error_sources(fidelity_problem, fidelity_parameters, ctx=None):
-    """reference src/FidelityCalculations.jl:161-218.  The cost/gradient evaluation runs on the GPU;
-    the optimiser itself (Optim.jl L-BFGS in the reference, out of the hot path) is scipy's L-BFGS-B.
-    Returns the scipy OptimizeResult (`.x` is `Optim.minimizer`)."""
+    """reference src/FidelityCalculations.jl:161-218.  The cost/gradient evaluation runs on the GPU.  With
+    `solver_algorithm = "device-lbfgs"` and enumerated regularisation functions the optimiser loop itself stays on the device
+    (batched L-BFGS, rg_lbfgs_batch); otherwise the optimiser (Optim.jl L-BFGS in the reference) is scipy's L-BFGS-B and arbitrary
+    regularisation callables are evaluated on the host.  Returns an OptimizeResult (`.x` is `Optim.minimizer`)."""
     from scipy.optimize import minimize
+    if fidelity_parameters.solver_algorithm == "device-lbfgs":
+        from scipy.optimize import OptimizeResult
+        prm = fidelity_parameters
+        ap = dict(prm.additional_parameters)
+        X, cost, iters, info = optimize_batch_device(fidelity_problem, np.asarray(prm.x_initial, dtype=np.float64)[:, None],
+                                                     prm.error_source_coeff, prm.regularization_functions, prm.regularization_coeff1,
+                                                     prm.regularization_coeff2, int(prm.iterations), float(ap.get("g_tol", 1e-8)),
+                                                     int(ap.get("history", 10)), ctx)
+        return OptimizeResult(x=X[:, 0].copy(), fun=float(cost[0]), nit=int(iters[0]), nfev=info["evaluations"], success=True,
+                              message="device L-BFGS", info=info)
     up = fidelity_problem.unitary_problem
     prm = fidelity_parameters
     assert len(prm.error_source_coeff) == len(up.error_sources)

@@ -608,3 +608,57 @@ def test_closure_problems_through_the_hstack_entry_points(gpu_ctx, errors, N):
     if errors:
         assert np.abs(U[3] - Ur[3]).max() < 2e-5 * np.abs(Ur[3]).max()
         assert np.abs(U[4] - Ur[4]).max() < 2e-4 * np.abs(Ur[4]).max()
+
+
+# ---- optimiser loop on the device -------------------------------------------------------------------
+def test_device_regularization_epilogue(gpu_ctx):
+    """k_regularize against the host functions (reference src/Regularization.jl:26-47,78-83,111-115; test/runtests.jl:9-45) and
+    against the literal restatement of calculate_common! with regularisation (src/FidelityCalculations.jl:174-197)."""
+    from robustgrape_b200 import regularization as R
+    from robustgrape_b200.unitary_calculations import device_problem
+    N, B = 57, 5
+    fp = detuned_problem(N, 2.0, ("amp",))            # p = 2 control rows, a = 2
+    X = np.stack([random_pulse(fp, 2, 90 + s) for s in range(B)], axis=1)
+    dp = device_problem(fp)
+    c0, g0 = dp.cost_and_grad_batch(X, [2e-4])
+    for funcs in ([R.regularization_cost, R.regularization_cost_phase], [R.regularization_cost_phase_sin2, R.regularization_cost],
+                  [R.regularization_cost_phase, R.regularization_cost_phase_sin2]):
+        c1s, c2s = [1e-3, 2e-2], [3e-3, 5e-4]
+        reg = list(zip(R.device_kinds(funcs), c1s, c2s))
+        c, g = dp.cost_and_grad_batch_reg(X, [2e-4], reg)
+        for b in range(B):
+            xm = X[:2 * N, b].reshape((2, N), order="F")
+            cost = c0[b]
+            grad = g0[:, b].copy()
+            for i, f in enumerate(funcs):
+                r1, j1, r2, j2 = f(xm[i].copy())
+                cost += c1s[i] * r1 + c2s[i] * r2
+                grad[i:2 * N:2] += c1s[i] * np.asarray(j1) + c2s[i] * np.asarray(j2)
+            assert abs(c[b] - cost) < 1e-12 * max(1.0, abs(cost))
+            assert np.abs(g[:, b] - grad).max() < 1e-12 * max(1.0, np.abs(grad).max())
+    # the test-suite form agrees with the oracle's restatement of test/runtests.jl:9-45
+    x = X[:2 * N:2, 0]
+    a, bq = R.regularization_cost_phase_sin2(x), ro.runtests_regularization_cost_phase(x)
+    assert abs(a[0] - bq[0]) < 1e-14 and np.abs(a[1] - bq[1]).max() < 1e-14 and abs(a[2] - bq[2]) < 1e-14 and np.abs(a[3] - bq[3]).max() < 1e-14
+
+
+def test_device_lbfgs_reaches_high_fidelity(gpu_ctx):
+    """reference test/runtests.jl:356-416 (40 L-BFGS iterations from a small random pulse -> infidelity < 1e-6) with the whole
+    optimiser loop on the device, for a batch of independent starts."""
+    from robustgrape_b200 import regularization as R
+    N, T0, B = 200, 2 * np.pi * 1.22, 24
+    fp = cz_problem(N, T0)
+    rng = np.random.default_rng(42)
+    X0 = np.concatenate([2 * np.pi * 0.001 * rng.random((N, B)), 2 * np.pi * rng.random((1, B))], axis=0)
+    X, cost, iters, info = rg.optimize_batch_device(fp, X0, [], [R.regularization_cost_phase_sin2], [1e-6], [1e-6],
+                                                    iterations=200, g_tol=3e-10)
+    F = rg.calculate_fidelity_and_derivatives_batch(fp, X, want_grad=False)[0]
+    assert np.median(1 - F) < 1e-6, (np.sort(1 - F), info)
+    assert (1 - F < 1e-6).mean() >= 0.75, (np.sort(1 - F), info)
+    assert info["evaluations"] <= 1 + 8 * info["iterations"] and info["iterations"] <= 200, info
+    # the single-pulse wrapper with the device optimiser
+    prm = rg.FidelityRobustGRAPEParameters(x_initial=X0[:, 0], regularization_functions=[R.regularization_cost_phase_sin2],
+                                           regularization_coeff1=[1e-6], regularization_coeff2=[1e-6], error_source_coeff=[], iterations=200,
+                                           solver_algorithm="device-lbfgs", additional_parameters={"g_tol": 3e-10})
+    res = rg.optimize_fidelity_and_error_sources(fp, prm)
+    assert 1 - rg.calculate_fidelity_and_derivatives(fp, res.x)[0] < 1e-6
