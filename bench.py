@@ -311,6 +311,69 @@ def run_dense(args):
     print(json.dumps(line), flush=True)
 
 
+def run_response(args):
+    """--workload C3 (BASELINE.json configs[2]): fidelity-response sweep over a 4096-point frequency grid (N = 500, amplitude + frequency
+    error sources, examples/time_optimal_cz.jl:60-67,82), the grid sharded over the ranks (no exchange inside a shard), rows all-gathered."""
+    import torch
+    import torch.distributed as dist
+    from robustgrape_b200._lib import Context
+    import robustgrape_b200 as rg
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = Context(local)
+    N, nfreq = 500, 4096
+    fp = make_problem(N, 2)
+    x = make_pulses(N, 1)[0]
+    freqs = np.linspace(0, 3, nfreq)
+    from robustgrape_b200.sharding import shard_range
+    first, hi = shard_range(nfreq, rank, world)
+    count = hi - first
+    full = torch.empty((world, 2, (nfreq + world - 1) // world), dtype=torch.float64, device=dev)
+
+    def sweep():
+        R = rg.calculate_fidelity_response(fp, x, freqs, ctx=ctx, first=first, count=count)          # (count, 2), blocking C-ABI call
+        mine = torch.zeros((2, full.shape[2]), dtype=torch.float64, device=dev)
+        mine[:, :count] = torch.from_numpy(np.ascontiguousarray(R.T)).to(dev)
+        if world > 1:
+            dist.all_gather_into_tensor(full.view(-1), mine.view(-1))
+        else:
+            full[0] = mine
+        torch.cuda.synchronize()
+        return R
+    for _ in range(args.warmup):
+        sweep()
+    if world > 1:
+        dist.barrier()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        R = sweep()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    ms = float(dt.item()) / args.steps * 1e3
+    if rank == 0:
+        line = {"metric": "fidelity-response sweeps/sec (4096-point grid)", "value": 1e3 / ms, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"C3: fidelity response, {nfreq} frequencies in [0, 3], N={N}, e=2 (amplitude, frequency), one pulse; grid "
+                                       f"sharded over {world} rank(s), rows all-gathered (NCCL)",
+                           "note": "a single sweep is ~0.8 GFLOP: launch/latency bound (SURVEY 8d says so); the time is host-call wall clock, "
+                                   "copies and the all-gather included"},
+                "e2e": {"value": 1e3 / ms, "unit": "sweeps/s", "h2d_bytes_per_step": int((N + 1) * 8 + nfreq * 8), "d2h_bytes_per_step": int(count * 2 * 8)},
+                "gpu_launches": int(ctx.launch_count)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,7 +386,7 @@ def main():
     ap.add_argument("--cpu-pulses-per-thread", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16"],
+    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16", "C3"],
                     help="C4 (default): multi-start CZ batch, the headline; C5 / d16: dense synthetic problem on the DMMA path (1 GPU)")
     ap.add_argument("--dense-ntimes", type=int, default=10000)
     ap.add_argument("--dense-norm", type=float, default=2.4, help="max_k ||dt H(k)||_1 of the dense workload (SURVEY 8d: 2.1 ... 5.4)")
@@ -338,6 +401,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "C3":
+        run_response(args)
         return
     if args.workload != "C4":
         run_dense(args)

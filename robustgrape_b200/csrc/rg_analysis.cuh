@@ -203,6 +203,9 @@ k_interaction_ops_par(const DevProblem P, const double* __restrict__ x, int L, i
 // shift = 1 reproduces calculate_fidelity_response (whose outer weight runs from 1, :269-271);
 // shift = 0 with w_n = 2 pi n / (M dt) reproduces calculate_fidelity_response_fft (fft / M*ifft, :328-339).
 // grid_mode: 0 = explicit frequencies; M > 0 = uniform FFT grid of M points (phases reduced exactly mod M).
+// Mapping: NS time slices x DD matrix elements per block, strided over the threads (d*d may exceed the block).  The phase of a
+// slice advances by a complex multiplication with e^{-i w dt NS} and is re-anchored with sincos every 32 terms, so a thread
+// spends 2 complex FMAs + 1 complex multiplication per term instead of a sincos; the trace epilogue is spread over d*d threads.
 template <int D>
 __global__ void __launch_bounds__(128)
 k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restrict__ freqs, int first, int count,
@@ -210,28 +213,31 @@ k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restr
     constexpr int DD = D * D;
     constexpr int NS = 128 / DD > 0 ? 128 / DD : 1;     // time slices per block
     __shared__ cplx sS[NS][DD], sT[NS][DD];
-    __shared__ cplx mS[DD], mT[DD];
+    __shared__ cplx mS[DD], mT[DD], SP[DD], TP[DD];
+    __shared__ double red[4][8];
     const int f = blockIdx.x, e = blockIdx.y;
     const int tid = threadIdx.x;
     const int n = first + f;
     const double w = M > 0 ? 0.0 : freqs[n];
     const double wdt = w * P.dt;
-    // (slice, element) pairs are strided over the block: d*d may exceed the block size (d = 12, 16)
+    auto phase = [&](int j, double& sn, double& cs) {     // e^{+i w dt j}
+        if (M > 0) { const long long r = ((long long)j * n) % M; sincospi(2.0 * (double)r / (double)M, &sn, &cs); }
+        else sincos(wdt * (double)j, &sn, &cs);
+    };
     for (int idx = tid; idx < NS * DD; idx += blockDim.x) {
         const int el = idx % DD, sl = idx / DD;
         cplx s = cmk(0, 0), t = cmk(0, 0);
         const cplx* Oe = O + (size_t)e * P.N * DD;
-        for (int j = sl; j < P.N; j += NS) {
-            double sn, cs;
-            if (M > 0) {
-                const long long r = ((long long)j * n) % M;
-                sincospi(2.0 * (double)r / (double)M, &sn, &cs);
-            } else {
-                sincos(wdt * (double)j, &sn, &cs);
-            }
+        double sn, cs, sn2, cs2;
+        phase(NS, sn2, cs2);                             // step of the slice: e^{+i w dt NS}
+        int cnt = 0;
+        cplx ph = cmk(1, 0);
+        for (int j = sl; j < P.N; j += NS, ++cnt) {
+            if ((cnt & 31) == 0) { phase(j, sn, cs); ph = cmk(cs, sn); }
             const cplx o = Oe[(size_t)j * DD + el];
-            cfma(s, cmk(cs, -sn), o);        // e^{-i w dt j}
-            cfma(t, cmk(cs, sn), o);         // e^{+i w dt j}
+            cfma(s, cconj(ph), o);           // e^{-i w dt j}
+            cfma(t, ph, o);                  // e^{+i w dt j}
+            ph = cmul(ph, cmk(cs2, sn2));
         }
         sS[sl][el] = s; sT[sl][el] = t;
     }
@@ -247,52 +253,65 @@ k_response(const DevProblem P, const cplx* __restrict__ O, const double* __restr
         mS[el] = a; mT[el] = b;
     }
     __syncthreads();
+    // SP = S P, TP = T P with P = (P0 != 0) (tr_mod(A) = tr(P0 A); :47-51)
+    for (int el = tid; el < DD; el += blockDim.x) {
+        const int i = el % D, j = el / D;
+        cplx a = cmk(0, 0), b = cmk(0, 0);
+        for (int q = 0; q < D; ++q) { const double p = P.Pm[q + D * j]; a.x += mS[i + D * q].x * p; a.y += mS[i + D * q].y * p; b.x += mT[i + D * q].x * p; b.y += mT[i + D * q].y * p; }
+        SP[el] = a; TP[el] = b;
+    }
+    __syncthreads();
+    // t1 = tr(P0 T SP), t2 = tr(P0 TP SP), t3 = tr(P0 TP), t4 = tr(P0 SP): entry (a, b) of P0 multiplies X[b][a]
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int el = tid; el < DD; el += blockDim.x) {
+        const int a = el % D, b = el / D;
+        const double p0 = P.P0raw[a + D * b];
+        if (p0 == 0.0) continue;
+        cplx x1 = cmk(0, 0), x2 = cmk(0, 0);
+        for (int q = 0; q < D; ++q) { cfma(x1, mT[b + D * q], SP[q + D * a]); cfma(x2, TP[b + D * q], SP[q + D * a]); }
+        v[0] += p0 * x1.x; v[1] += p0 * x1.y; v[2] += p0 * x2.x; v[3] += p0 * x2.y;
+        v[4] += p0 * TP[b + D * a].x; v[5] += p0 * TP[b + D * a].y; v[6] += p0 * SP[b + D * a].x; v[7] += p0 * SP[b + D * a].y;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+    if ((tid & 31) == 0)
+        for (int q = 0; q < 8; ++q) red[tid >> 5][q] = v[q];
+    __syncthreads();
     if (tid == 0) {
-        // traces with P0 (tr_mod(A) = tr(P0 A)) and P = (P0 != 0); PP = P0 P is precomputed
+        double t[8];
+        for (int q = 0; q < 8; ++q) t[q] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
         const double Dt = P.Dtr, DD1 = Dt * (Dt + 1.0);
-        cplx SP[DD], TP[DD];
-        for (int j = 0; j < D; ++j)
-            for (int i = 0; i < D; ++i) {
-                cplx a = cmk(0, 0), b = cmk(0, 0);
-                for (int q = 0; q < D; ++q) { const double p = P.Pm[q + D * j]; a.x += mS[i + D * q].x * p; a.y += mS[i + D * q].y * p; b.x += mT[i + D * q].x * p; b.y += mT[i + D * q].y * p; }
-                SP[i + D * j] = a; TP[i + D * j] = b;
-            }
-        // t1 = tr(P0 T S P), t2 = tr(P0 T P S P), t3 = tr(P0 T P), t4 = tr(P0 S P)
-        cplx t1 = cmk(0, 0), t2 = cmk(0, 0), t3 = cmk(0, 0), t4 = cmk(0, 0);
-        const double* P0 = P.P0raw;
-        for (int a = 0; a < D; ++a)
-            for (int b = 0; b < D; ++b) {
-                const double p0 = P0[a + D * b];         // P0[a][b] multiplies X[b][a]
-                if (p0 == 0.0) continue;
-                cplx x1 = cmk(0, 0), x2 = cmk(0, 0);
-                for (int q = 0; q < D; ++q) { cfma(x1, mT[b + D * q], SP[q + D * a]); cfma(x2, TP[b + D * q], SP[q + D * a]); }
-                t1.x += p0 * x1.x; t1.y += p0 * x1.y;
-                t2.x += p0 * x2.x; t2.y += p0 * x2.y;
-                t3.x += p0 * TP[b + D * a].x; t3.y += p0 * TP[b + D * a].y;
-                t4.x += p0 * SP[b + D * a].x; t4.y += p0 * SP[b + D * a].y;
-            }
-        const double r = t1.x / Dt - t2.x / DD1 - (t3.x * t4.x - t3.y * t4.y) / DD1;
+        const double r = t[0] / Dt - t[2] / DD1 - (t[4] * t[6] - t[5] * t[7]) / DD1;
         R[(size_t)e * count + f] = P.dt * P.dt * r;
     }
 }
 
-// s[k,e] = tr(P0 O_k^e); out[k,e] = Re(dt * sum_{j<=k} s[j,e] / D)   (cumsum is linear in the trace)
+// s[k,e] = tr(P0 O_k^e); out[k,e] = Re(dt * sum_{j<=k} s[j,e] / D)   (cumsum is linear in the trace, :374,384-388).
+// One block per error source: threads take the traces of contiguous runs of steps, then a block scan of the run totals.
 template <int D>
-__global__ void k_expectation(const DevProblem P, const cplx* __restrict__ O, double* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+k_expectation(const DevProblem P, const cplx* __restrict__ O, double* __restrict__ out) {
     constexpr int DD = D * D;
-    const int e = blockIdx.x;
-    if (threadIdx.x != 0) return;
+    __shared__ double tot[256];
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int per = (P.N + nt - 1) / nt;
+    const int k0 = min(P.N, tid * per), k1 = min(P.N, k0 + per);
     const double* P0 = P.P0raw;
-    cplx acc[DD];
-    for (int i = 0; i < DD; ++i) acc[i] = cmk(0, 0);
-    for (int k = 0; k < P.N; ++k) {
+    auto tr = [&](int k) {
         const cplx* o = O + ((size_t)e * P.N + k) * DD;
-        double tr = 0.0;
+        double t = 0.0;
         for (int j = 0; j < D; ++j)
-            for (int i = 0; i < D; ++i) {
-                acc[i + D * j] = cadd(acc[i + D * j], o[i + D * j]);     // cumsum of the operators (:374)
-                tr += P0[j + D * i] * acc[i + D * j].x;                  // Re tr(P0 S) = sum P0[j][i] Re S[i][j]
-            }
-        out[(size_t)e * P.N + k] = P.dt * tr / P.Dtr;
-    }
+            for (int i = 0; i < D; ++i) t += P0[j + D * i] * o[i + D * j].x;       // Re tr(P0 O) = sum P0[j][i] Re O[i][j]
+        return t;
+    };
+    double run = 0.0;
+    for (int k = k0; k < k1; ++k) run += tr(k);
+    tot[tid] = run;
+    __syncthreads();
+    if (tid == 0) { double acc = 0.0; for (int q = 0; q < nt; ++q) { const double v = tot[q]; tot[q] = acc; acc += v; } }   // exclusive prefix
+    __syncthreads();
+    double acc = tot[tid];
+    for (int k = k0; k < k1; ++k) { acc += tr(k); out[(size_t)e * P.N + k] = P.dt * acc / P.Dtr; }
 }

@@ -665,7 +665,7 @@ static int launch_response(rg_problem* pr, const double* dfreqs, int first, int 
 template <int D>
 static int launch_expectation(rg_problem* pr, double* dOut) {
     KTimer kt(pr->ctx, RG_K_ANALYSIS);
-    k_expectation<D><<<pr->dp.e, 32, 0, pr->ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dOut);
+    k_expectation<D><<<pr->dp.e, 256, 0, pr->ctx->stream>>>(pr->dp, pr->dO.as<cplx>(), dOut);
     return RG_OK;
 }
 

@@ -350,6 +350,27 @@ def test_nine_level_rydberg_model(gpu_ctx):
     O = rg.calculate_interaction_error_operators(fp.unitary_problem, x)
     Or = ro.calculate_interaction_error_operators(fp.unitary_problem, x)
     assert np.abs(O - Or).max() < 1e-11 * np.abs(Or).max()
+    # response / expectation kernels at d*d = 81 elements per operator (strided element loop)
+    freqs = np.linspace(0, 2.5, 7)
+    R, Rr = rg.calculate_fidelity_response(fp, x, freqs), ro.calculate_fidelity_response(fp, x, freqs)
+    assert np.abs(R - Rr).max() < 1e-10 * np.abs(Rr).max()
+    E, Er = rg.calculate_expectation_values(fp, x), ro.calculate_expectation_values(fp, x)
+    assert np.abs(E - Er).max() < 1e-12 * max(1.0, np.abs(Er).max())
+
+
+def test_analysis_entry_points_fail_closed_on_the_dense_path(gpu_ctx):
+    """ndim > 10 runs the DMMA path, which implements the fused fidelity/gradient entry points only: the analysis and
+    materialising entry points must refuse (RG_ERR_UNSUPPORTED), never return unfilled buffers."""
+    from cases import dense_random_problem
+    fp = dense_random_problem(12, 5, nparam=1, nerr=1, seed=3)
+    x = np.random.default_rng(1).uniform(-1, 1, 5)
+    for call in (lambda: rg.calculate_fidelity_response(fp, x, np.array([0.0, 1.0])),
+                 lambda: rg.calculate_expectation_values(fp, x),
+                 lambda: rg.calculate_interaction_error_operators(fp.unitary_problem, x),
+                 lambda: rg.calculate_unitary_and_derivatives(fp.unitary_problem, x)):
+        with pytest.raises(_lib.RGError) as ei:
+            call()
+        assert ei.value.code == _lib.RG_ERR_UNSUPPORTED
 
 
 def test_structured_path_with_non_diagonal_target_and_projector(gpu_ctx):
