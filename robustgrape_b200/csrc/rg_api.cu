@@ -21,7 +21,10 @@ const DimOps* rg_dim_ops(int d) {
     }
 }
 
+// message of the last failure that has no context to attach to (rg_ctx_create); guarded: contexts may be created concurrently
 static std::string g_global_err;
+static std::mutex g_global_err_mutex;
+static void set_global_err(const std::string& m) { std::lock_guard<std::mutex> l(g_global_err_mutex); g_global_err = m; }
 
 extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     if (!out) return RG_ERR_INVALID;
@@ -29,16 +32,16 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
-        g_global_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        set_global_err(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
         cudaGetLastError();
         return RG_ERR_CUDA;
     }
-    if (device < 0 || device >= n) { g_global_err = "device index out of range"; return RG_ERR_INVALID; }
+    if (device < 0 || device >= n) { set_global_err("device index out of range"); return RG_ERR_INVALID; }
     rg_ctx* c = new rg_ctx();
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) { delete c; g_global_err = "cudaSetDevice failed"; return RG_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; set_global_err("cudaSetDevice failed"); return RG_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete c; g_global_err = "cudaStreamCreate failed"; return RG_ERR_CUDA;
+        delete c; set_global_err("cudaStreamCreate failed"); return RG_ERR_CUDA;
     }
     c->stream = c->own_stream;
     cudaMalloc(&c->d_status, sizeof(int));
@@ -51,7 +54,7 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (const char* s = getenv("RG_WS_LIMIT_GB")) c->ws_limit = (size_t)atof(s) * ((size_t)1 << 30);
-    if (cudaGetLastError() != cudaSuccess) { g_global_err = "context initialisation failed"; delete c; return RG_ERR_CUDA; }
+    if (cudaGetLastError() != cudaSuccess) { set_global_err("context initialisation failed"); delete c; return RG_ERR_CUDA; }
     *out = c;
     return RG_OK;
 }

@@ -446,7 +446,10 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
         }
         __syncthreads();
     }
-    if (!do_grad) { if (Kmax == 99) atomicOr(status, 2); return; }          // F / F_d2err only
+    if (!do_grad) {          // F / F_d2err only
+        if (Kmax == 99) { atomicOr(status, 2); if (live) Fout[ERR ? (size_t)b * ne + es : (size_t)b] = __longlong_as_double(0x7ff8000000000000ll); }
+        return;
+    }
     // ---- 4. co-states at the end of this lane's chunk
     Q g, h;
     {
@@ -551,5 +554,10 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             outb[(size_t)P.p * P.N + lane] = s + (ERR ? 1.0 : scale0T) * addT[lane];
         }
     }
-    if (Kmax == 99) atomicOr(status, 2);
+    if (Kmax == 99) {
+        // ||dt H|| outside the closed-form range: flag it, and poison this pulse's fidelity output so that callers of the
+        // asynchronous *_dev entry points cannot consume an inaccurate value before they see the status (fail closed)
+        atomicOr(status, 2);
+        if (live) Fout[ERR ? (size_t)b * ne + es : (size_t)b] = __longlong_as_double(0x7ff8000000000000ll);
+    }
 }

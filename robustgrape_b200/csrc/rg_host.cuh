@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -225,6 +226,8 @@ static int set_smem(rg_ctx* ctx, K kern, size_t bytes) {
     // keyed by (kernel address, device): instantiations with the same signature share the type K
     struct Granted { const void* fn; int dev; size_t bytes; };
     static std::vector<Granted> granted;
+    static std::mutex granted_mutex;                 // contexts on different host threads share this cache
+    std::lock_guard<std::mutex> lock(granted_mutex);
     const void* fn = reinterpret_cast<const void*>(kern);
     for (auto& g : granted)
         if (g.fn == fn && g.dev == ctx->device) {

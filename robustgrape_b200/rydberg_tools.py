@@ -184,3 +184,15 @@ def rydberg_full_h0(Omega1=1.0, Omega2=1.0, delta1=0.0, delta2=0.0, B=0.0, phase
     if diag:
         terms.append(Term(1.0, (), diag, OWNER_H0))
     return TermHamiltonian(9, terms)
+
+
+def rydberg_h0_ensemble(model="symmetric_blockaded", phase_index=0, amp_index=1, delta_index=2):
+    """H0(time_step, phi, x_add) = rydberg_hamiltonian_<model>(phi[phase_index], x_add[amp_index], x_add[delta_index]): the static
+    amplitude deviation and detuning are *per-pulse* additional parameters, so a batch of pulses is an error ensemble -- every
+    sample of (eps, delta) is one column of X, evaluated (and sharded over GPUs) like any other batch.  This is the batched form
+    of the H0(+-eps2) variants of reference test/runtests.jl:228-289 (`north_star`: "error-ensemble samples")."""
+    ndim, up, ryd = _model(model)
+    amp = Factor.var(S_ADD, amp_index, 1.0, 1.0)          # (1 + eps)
+    terms = _drive_terms(up, phase_index, extra=(amp,))
+    terms.append(Term(1.0, (Factor.var(S_ADD, delta_index),), tuple((r, r, 1.0) for r in ryd), OWNER_H0))
+    return TermHamiltonian(ndim, terms)
