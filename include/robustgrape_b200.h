@@ -212,6 +212,17 @@ int rg_gather_wait(rg_ctx* ctx, int32_t slot);
  * without stalling the evaluation stream. */
 int rg_gather_wait_on(rg_ctx* ctx, int32_t slot, void* cuda_stream);
 
+/* Which kernel family a cost/gradient evaluation of this problem takes, as a short string (diagnostics, benchmarks and tests; the
+ * reference has no counterpart -- there is one generic path, src/UnitaryCalculations.jl:20-155):
+ *   "fused_q_pc"  one launch per role, phase-only drive class (step constants evaluated once, one sincos per step and sweep)
+ *   "fused_q"     one launch per role, closed-form 2 x 2 blocks recomputed per step
+ *   "block2"      workspace-free three-kernel path (blocks with diagonal terms)
+ *   "steps_t"     thread-per-step propagators with a step-matrix workspace (d <= 5)
+ *   "group"       general shared-memory kernels (scaling and squaring, non-Hermitian, d <= 10)
+ *   "dense"       planar DMMA path (d > 10)        "hstack"  host-evaluated Hamiltonian stacks
+ * Returns RG_OK; the string is truncated to len - 1 characters. */
+int rg_problem_path(rg_problem* prob, char* buf, int32_t len);
+
 /* FP64 peak microbenchmarks (DFMA loop, DMMA m8n8k4 loop) on the context device: TFLOP/s. */
 int rg_measure_fp64_peak(rg_ctx* ctx, double seconds, double* dfma_tflops, double* dmma_tflops);
 

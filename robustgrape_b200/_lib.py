@@ -88,6 +88,7 @@ SIGNATURES = {
     "rg_gather_wait": (C.c_int, [_vp, C.c_int32]),
     "rg_gather_wait_on": (C.c_int, [_vp, C.c_int32, _vp]),
     "rg_measure_fp64_peak": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+    "rg_problem_path": (C.c_int, [_vp, C.c_char_p, C.c_int32]),
 }
 
 _lib = None
@@ -319,6 +320,13 @@ class Problem:
             self.ctx.check(self.ctx.lib.rg_problem_create(self.ctx.handle, C.byref(self._desc), C.byref(h)))
             self._handles[p] = h
         return self._handles[p], p
+
+    def path(self, nx):
+        """Kernel family an evaluation with len(x) == nx takes (include/robustgrape_b200.h: rg_problem_path)."""
+        h, _ = self.handle_for(nx)
+        buf = C.create_string_buffer(32)
+        self.ctx.check(self.ctx.lib.rg_problem_path(h, buf, 32))
+        return buf.value.decode()
 
     def close(self):
         for h in self._handles.values():

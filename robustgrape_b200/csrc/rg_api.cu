@@ -391,6 +391,44 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
             if (!((cm >> (en.row + d * en.col)) & 1ull)) inside = false;
         pr->costate_in_pattern = inside ? 1 : 0;
         pr->tri_ok = 1;
+        // Phase-only drive class (DevProblem::pc): every term with upper-triangle entries is coef x [one error-amplitude factor] x E,
+        // E the same list of EXPI factors in every such term, and no perturbation variable enters E twice.
+        {
+            bool ok = !getenv("RG_NO_PC") || atoi(getenv("RG_NO_PC")) == 0;
+            int first = -1;
+            std::vector<DevFactor> ph;
+            for (int t = 0; t < P.nterms && ok; ++t) {
+                if (!used[t]) continue;
+                std::vector<DevFactor> mine;
+                int nerrf = 0;
+                for (int f = 0; f < ht[t].nf; ++f) {
+                    const DevFactor& ft = ht[t].f[f];
+                    if (ft.kind == RG_F_EXPI) mine.push_back(ft);
+                    else if (ft.kind == RG_F_ERR || ft.kind == RG_F_ERR1P_M1) ++nerrf;
+                    else ok = false;
+                }
+                if (ht[t].owner == RG_OWNER_H0 ? nerrf != 0 : nerrf > 1) ok = false;
+                if (first < 0) { first = t; ph = mine; }
+                else {
+                    if (mine.size() != ph.size()) ok = false;
+                    for (size_t f = 0; ok && f < mine.size(); ++f)
+                        if (mine[f].space != ph[f].space || mine[f].index != ph[f].index || mine[f].scale != ph[f].scale ||
+                            mine[f].offset != ph[f].offset) ok = false;
+                }
+            }
+            if (first < 0) ok = false;
+            for (int v = 0; v < RG_MAX_VARS; ++v) P.pc_vscale[v] = 0.0;
+            for (int v = 0; v < P.nvar && ok; ++v) {
+                int hits = 0;
+                for (auto& ft : ph)
+                    if (ft.space == P.var_space[v] && ft.index == P.var_index[v]) { P.pc_vscale[v] = ft.scale; ++hits; }
+                if (hits > 1) ok = false;
+            }
+            P.pc = ok ? 1 : 0;
+            P.pc_nf = ok ? (int)ph.size() : 0;
+            for (int f = 0; f < P.pc_nf; ++f) P.pc_f[f] = ph[f];
+            P.pc_consts = nullptr;
+        }
     }
     if (cudaGetLastError() != cudaSuccess || !P.terms || !P.table) return fail(RG_ERR_CUDA, "descriptor upload failed");
     *out = pr;

@@ -1,5 +1,21 @@
 // rg_api_analysis.inl -- host side of the analysis entry points (included by rg_api.cu).
 
+extern "C" int rg_problem_path(rg_problem* pr, char* buf, int32_t len) {
+    if (!pr || !buf || len <= 0) return RG_ERR_INVALID;
+    cudaSetDevice(pr->ctx->device);
+    const char* s = "group";
+    if (pr->is_hstack) s = "hstack";
+    else if (pr->big_dp) s = "dense";
+    else if (rg_use_fq(pr)) {
+        const int rc = rg_fq_prepare(pr);
+        if (rc) return rc;
+        s = pr->dp.pc ? "fused_q_pc" : "fused_q";
+    } else if (rg_use_b2(pr)) s = "block2";
+    else if (pr->tri_ok && pr->dp.d <= 5 && !pr->force_group) s = "steps_t";
+    snprintf(buf, (size_t)len, "%s", s);
+    return RG_OK;
+}
+
 extern "C" int rg_measure_fp64_peak(rg_ctx* ctx, double seconds, double* dfma_tflops, double* dmma_tflops) {
     if (!ctx) return RG_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));

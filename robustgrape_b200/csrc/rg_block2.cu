@@ -56,3 +56,11 @@ int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, i
     default: pr->ctx->err = "internal: fused quaternion path without an eligible pattern"; return RG_ERR_INVALID;
     }
 }
+// evaluates the phase-only constants if the problem is in that class (clears dp.pc when they are out of range)
+int rg_fq_prepare(rg_problem* pr) {
+    switch (rg_fq_pattern(pr)) {
+    case 1: return rg_fq_ops_p1.prepare(pr);
+    case 3: return rg_fq_ops_p3.prepare(pr);
+    default: return RG_OK;
+    }
+}

@@ -15,6 +15,7 @@ struct B2Ops {
 };
 struct FQOps {
     int (*launch)(rg_problem*, const DevProblem&, int, const double*, int, double*, int, double*, double, double, int);
+    int (*prepare)(rg_problem*);
 };
 extern const B2Ops rg_b2_ops_p1, rg_b2_ops_p2, rg_b2_ops_p3, rg_b2_ops_p4;
 extern const FQOps rg_fq_ops_p1, rg_fq_ops_p3;

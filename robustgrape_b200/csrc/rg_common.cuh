@@ -52,6 +52,16 @@ struct DevProblem {
     int wsm;             // complex elements stored per step matrix (d*d, or the closure pattern's nnz)
     int wsB;             // pulses in the current launch: the workspace is object-major, ws[obj][b][k][wsm]
     unsigned long long cmask;   // closure pattern of the stored matrices: bit (i + d*j)
+    // Phase-only drive class (rg_fusedq.cuh, PC kernels): every upper-triangle entry of H0 and of every error Hamiltonian is
+    // (constant | error amplitude) x E(x), with E the same product of EXPI factors everywhere.  Then |w| of every 2 x 2 block is
+    // the same at every time step and so are cos/sinc and all their finite differences: they are evaluated once per problem
+    // (k_fqc_consts) and a step costs one sincos.
+    int pc;                     // 1: class detected on the host
+    int pc_nf;                  // EXPI factors of E
+    DevFactor pc_f[RG_MAX_FACTORS];
+    double pc_vscale[RG_MAX_VARS];   // d(arg of E)/d(var v): scale of the factor that depends on v, 0 if none
+    const double2* pc_consts;   // [(1 + 2 e)][2 NB]: reference propagator (a_n, b_n conj(E_ref)); per error source its difference at
+                                // eps and at eps2
 };
 
 // ---------------------------------------------------------------------------------------

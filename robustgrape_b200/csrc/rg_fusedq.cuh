@@ -150,6 +150,181 @@ __device__ __forceinline__ int q_step(const DevProblem& P, const StagedPlan& sp,
     return Kmax;
 }
 
+
+// ---- phase-only drive class (DevProblem::pc) ---------------------------------------------------------------------------
+// Every block of every step propagator, and of each of its finite differences, is [[c, s E_k], [-s conj(E_k), c]] with a *real*
+// step-independent c and a step-independent complex s: quaternions with a real diagonal part, 12 instead of 16 multiplications
+// per product.  c and s come from k_fqc_consts (the closed-form series in difference arithmetic, evaluated once per problem at the
+// reference point x = 0); the variable differences are exact too:  U(phi + h) - U(phi) = (0, s E_k (e^{i sigma h} - 1)).
+template <int NB> struct QR { double a[NB]; cplx b[NB]; };
+// r (+)= u q
+template <int NB, bool ACC = false>
+__device__ __forceinline__ void qr_mul(QS<NB>& r, const QR<NB>& u, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = ACC ? r.a[n] : cmk(0.0, 0.0), b = ACC ? r.b[n] : cmk(0.0, 0.0);
+        a.x = fma(u.a[n], q.a[n].x, a.x); a.y = fma(u.a[n], q.a[n].y, a.y);
+        cfma(a, cmk(-u.b[n].x, -u.b[n].y), cconj(q.b[n]));
+        b.x = fma(u.a[n], q.b[n].x, b.x); b.y = fma(u.a[n], q.b[n].y, b.y);
+        cfma(b, u.b[n], cconj(q.a[n]));
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+// r = u^dag q,  u^dag = (a, -b)
+template <int NB>
+__device__ __forceinline__ void qr_adjmul(QS<NB>& r, const QR<NB>& u, const QS<NB>& q) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = cmk(u.a[n] * q.a[n].x, u.a[n] * q.a[n].y), b = cmk(u.a[n] * q.b[n].x, u.a[n] * q.b[n].y);
+        cfma(a, u.b[n], cconj(q.b[n]));
+        cfma(b, cmk(-u.b[n].x, -u.b[n].y), cconj(q.a[n]));
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+// r (+)= g u  (right multiplication):  (ga ua - gb conj(ub), ga ub + gb ua)
+template <int NB, bool ACC = false>
+__device__ __forceinline__ void qr_rmul(QS<NB>& r, const QS<NB>& g, const QR<NB>& u) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx a = ACC ? r.a[n] : cmk(0.0, 0.0), b = ACC ? r.b[n] : cmk(0.0, 0.0);
+        a.x = fma(u.a[n], g.a[n].x, a.x); a.y = fma(u.a[n], g.a[n].y, a.y);
+        cfma(a, cmk(-g.b[n].x, -g.b[n].y), cconj(u.b[n]));
+        b.x = fma(u.a[n], g.b[n].x, b.x); b.y = fma(u.a[n], g.b[n].y, b.y);
+        cfma(b, g.a[n], u.b[n]);
+        r.a[n] = a; r.b[n] = b;
+    }
+}
+// Re tr(g X c) for X = (0, beta):  -2 Re( sum_n beta_n W_n ),  W_n = ga conj(cb) + conj(gb ca)
+template <int NB, bool ACC = false>
+__device__ __forceinline__ void qr_w(cplx (&w)[NB], const QS<NB>& g, const QS<NB>& c) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+        cplx t = ACC ? w[n] : cmk(0.0, 0.0);
+        cfma(t, g.a[n], cconj(c.b[n]));
+        // conj(gb ca) = (gb.x ca.x - gb.y ca.y, -(gb.x ca.y + gb.y ca.x))
+        t.x = fma(g.b[n].x, c.a[n].x, t.x); t.x = fma(-g.b[n].y, c.a[n].y, t.x);
+        t.y = fma(-g.b[n].x, c.a[n].y, t.y); t.y = fma(-g.b[n].y, c.a[n].x, t.y);
+        w[n] = t;
+    }
+}
+// sin and cos of one argument for the per-step phase: Cody-Waite reduction by pi/2 in three fused steps, the two minimax
+// polynomials of fdlibm's k_sin / k_cos on [-pi/4, pi/4], quadrant fix-up with selects.  Measured against long-double
+// sinl/cosl on 2e7 random arguments per range (|x| < 7, 100, 1e5): max error 1.58 ulp.  The library sincos() costs ~250 SASS
+// instructions per call here (coefficient tables through LDC, constants through UMOV pairs under the register cap), and after
+// the closed-form step constants the two calls per step were half of the kernel; this one is ~35.  |x| > 1e5 takes sincos().
+__constant__ double c_sc[16] = {
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,                      // 2/pi, pi/2 split in three
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,                                                       // S6 .. S1
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};                                                      // C6 .. C1
+static __device__ __noinline__ double2 rg_sincos_slow(double x) { double2 r; sincos(x, &r.y, &r.x); return r; }
+// (coefficients come from the constant bank as DFMA operands: as literals each one costs a UMOV pair per use)
+__device__ __forceinline__ void rg_sincos(double x, double& s, double& c) {
+    if (fabs(x) > 1.0e5) { const double2 r = rg_sincos_slow(x); s = r.y; c = r.x; return; }
+    const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: the fma rounds x * 2/pi to the nearest integer
+    const double t = fma(x, c_sc[0], MAGIC);
+    const int q = __double2loint(t);
+    const double j = t - MAGIC;
+    double r = fma(-j, c_sc[1], x);
+    r = fma(-j, c_sc[2], r);
+    r = fma(-j, c_sc[3], r);
+    const double z = r * r;
+    double ps = fma(z, c_sc[4], c_sc[5]);
+    ps = fma(z, ps, c_sc[6]); ps = fma(z, ps, c_sc[7]); ps = fma(z, ps, c_sc[8]); ps = fma(z, ps, c_sc[9]);
+    const double sr = fma(r * z, ps, r);
+    double pc = fma(z, c_sc[10], c_sc[11]);
+    pc = fma(z, pc, c_sc[12]); pc = fma(z, pc, c_sc[13]); pc = fma(z, pc, c_sc[14]); pc = fma(z, pc, c_sc[15]);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    // sign flips on the high words: s negative in quadrants 2, 3; c negative in quadrants 1, 2
+    s = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
+    c = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
+}
+// E_k = prod_f exp(i (scale_f v_f + offset_f)); the common case (one factor in a main parameter) is hoisted into PCArg
+struct PCArg { int fast, idx, plain; double sc, of; int v1, vidx; double vsc; };
+__device__ __forceinline__ PCArg pc_arg(const DevProblem& P) {
+    PCArg a;
+    a.fast = (P.pc_nf == 1 && P.pc_f[0].space == RG_S_MAIN) ? 1 : 0;
+    a.idx = P.pc_f[0].index; a.sc = P.pc_f[0].scale; a.of = P.pc_f[0].offset;
+    a.plain = (a.sc == 1.0 && a.of == 0.0) ? 1 : 0;
+    a.v1 = (P.nvar == 1 && P.var_space[0] == RG_S_MAIN) ? 1 : 0;      // one perturbation variable, a main parameter
+    a.vidx = P.var_index[0]; a.vsc = P.pc_vscale[0];
+    return a;
+}
+static __device__ __noinline__ void pc_phase_general(const DevProblem& P, const double* xk, const double* xadd, cplx* Eout) {
+    cplx E = cmk(1.0, 0.0);
+    for (int f = 0; f < P.pc_nf; ++f) {
+        const DevFactor& ft = P.pc_f[f];
+        const double v = (ft.space == RG_S_MAIN) ? xk[ft.index] : xadd[ft.index];
+        const bool plain = (ft.scale == 1.0 && ft.offset == 0.0);
+        double s, c;
+        rg_sincos(plain ? v : fma(ft.scale, v, ft.offset), s, c);
+        E = (f == 0) ? cmk(c, s) : cmul(E, cmk(c, s));
+    }
+    *Eout = E;
+}
+__device__ __forceinline__ cplx pc_phase(const DevProblem& P, const PCArg& a, const double* xk, const double* xadd) {
+    cplx E;
+    if (a.fast) {
+        const double v = xk[a.idx];
+        rg_sincos(a.plain ? v : fma(a.sc, v, a.of), E.y, E.x);
+    } else pc_phase_general(P, xk, xadd, &E);
+    return E;
+}
+// e^{i sigma_v h} - 1 with h = fl(val + e) - val the step actually taken in variable v (src/UnitaryCalculations.jl:50)
+__device__ __forceinline__ cplx pc_eta(const DevProblem& P, const double* xk, const double* xadd, int v, double e) {
+    const double val = (P.var_space[v] == RG_S_MAIN) ? xk[P.var_index[v]] : xadd[P.var_index[v]];
+    const double h = __dsub_rn(__dadd_rn(val, e), val);
+    return expm1i(P.pc_vscale[v] * h);
+}
+// Constants of the class, one thread: reference propagators at x = 0, x_add = 0 through the generic closed-form path.
+//   out[0 .. 2NB)                 (a_n, b_n conj(E_ref)) of U
+//   out[(1 + 2 es) 2NB ...)       first difference in error source es at eps      (:66-70)
+//   out[(2 + 2 es) 2NB ...)       first difference in error source es at eps2     (the b slot of :76-83)
+// flag[0] = 1 if a block is outside the closed-form range (the host then keeps the generic kernel, which reports it).
+template <int D, unsigned UMASK>
+__global__ void k_fqc_consts(const DevProblem P, const TriPlanDev tp, cplx* __restrict__ out, int* __restrict__ flag) {
+    constexpr int NB = b2_nblocks(D, UMASK);
+    extern __shared__ cplx smem[];
+    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    if (threadIdx.x != 0) return;
+    double xk[RG_MAX_MAIN], xadd[RG_MAX_ADD];
+    for (int i = 0; i < RG_MAX_MAIN; ++i) xk[i] = 0.0;
+    for (int i = 0; i < RG_MAX_ADD; ++i) xadd[i] = 0.0;
+    const TrigSlots tr{0, 0.0, 1.0, 0.0, 1.0};
+    const cplx Er = cconj(pc_phase(P, pc_arg(P), xk, xadd));
+    int Kmax = 0;
+    {
+        QS<NB> u[1];
+        Kmax = max(Kmax, q_step<D, UMASK, 0>(P, sp, xk, xadd, 0, B2_VALUE, 0, 0, u, tr));
+        for (int n = 0; n < NB; ++n) { out[2 * n] = u[0].a[n]; out[2 * n + 1] = cmul(u[0].b[n], Er); }
+    }
+    for (int es = 0; es < P.e; ++es) {
+        cplx* o1 = out + (size_t)(1 + 2 * es) * 2 * NB;
+        cplx* o2 = out + (size_t)(2 + 2 * es) * 2 * NB;
+        QS<NB> ue[2];
+        Kmax = max(Kmax, q_step<D, UMASK, 1>(P, sp, xk, xadd, 0, B2_ERR, 0, es, ue, tr));
+        for (int n = 0; n < NB; ++n) { o1[2 * n] = ue[1].a[n]; o1[2 * n + 1] = cmul(ue[1].b[n], Er); }
+        for (int n = 0; n < NB; ++n) { o2[2 * n] = cmk(0.0, 0.0); o2[2 * n + 1] = cmk(0.0, 0.0); }
+        if (P.nvar > 0) {
+            QS<NB> u4[4];
+            Kmax = max(Kmax, q_step<D, UMASK, 2>(P, sp, xk, xadd, 0, B2_MIXED, 0, es, u4, tr));
+            for (int n = 0; n < NB; ++n) { o2[2 * n] = u4[2].a[n]; o2[2 * n + 1] = cmul(u4[2].b[n], Er); }
+        }
+    }
+    flag[0] = (Kmax == 99) ? 1 : 0;
+}
+template <int NB> __device__ __forceinline__ void pc_load(QR<NB>& u, const cplx* __restrict__ c) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { u.a[n] = c[2 * n].x; u.b[n] = c[2 * n + 1]; }
+}
+// u = (ref.a, ref.b E)
+template <int NB> __device__ __forceinline__ void pc_rot(QR<NB>& u, const QR<NB>& ref, cplx E) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) { u.a[n] = ref.a[n]; u.b[n] = cmul(ref.b[n], E); }
+}
+
 // shared-memory slot of one pulse (in complex numbers)
 template <int D, unsigned UMASK> struct FQLayout {
     static constexpr int NB = b2_nblocks(D, UMASK);
@@ -160,10 +335,10 @@ template <int D, unsigned UMASK> struct FQLayout {
     static constexpr int acc = 4 * RG_MAX_ADD;              // per warp x_add partial sums (as doubles: 4 warps x RG_MAX_ADD -> /2 cplx) + addT
     static constexpr int slot = alg + tot + fin + acc + 1;
 };
-__host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int nent) {
+__host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int nent, bool pc = false) {
     const int DD = d * d;
     const size_t slot = (size_t)(14 * DD + d + 1) + 16 * nb + 4 * nb + 4 * RG_MAX_ADD + 1;
-    return staged_plan_bytes(nterms, nent, d) + 4 * slot * sizeof(cplx);
+    return (pc ? 0 : staged_plan_bytes(nterms, nent, d)) + 4 * slot * sizeof(cplx);      // the PC kernels never read the term plan
 }
 
 
@@ -192,7 +367,7 @@ struct FQDiag {
         if constexpr (!ERR) {
 #pragma unroll
             for (int l = 0; l < D; ++l)
-                if (b2_partner(D, UMASK, l) < 0) { t.x += pw[l] * u0[l].x; t.y -= pw[l] * u0[l].y; }      // U_ll = 1
+                if (B2P<D, UMASK>::partner(l) < 0) { t.x += pw[l] * u0[l].x; t.y -= pw[l] * u0[l].y; }      // U_ll = 1
         }
         return t;
     }
@@ -233,7 +408,7 @@ struct FQDiag {
         if constexpr (!ERR) {
 #pragma unroll
             for (int l = 0; l < D; ++l)
-                if (b2_partner(D, UMASK, l) < 0) s += pw[l] * roww[l] * (pw[l] != 0.0 ? 1.0 : 0.0);
+                if (B2P<D, UMASK>::partner(l) < 0) s += pw[l] * roww[l] * (pw[l] != 0.0 ? 1.0 : 0.0);
         }
         return s;
     }
@@ -252,19 +427,29 @@ struct FQDiag {
 #ifndef RG_FQ_CTAS
 #define RG_FQ_CTAS 4          // 128-register cap: measured on B200 equal at 8192 pulses (0.514 vs 0.510 ms), 18-23 % faster at 1024-2048
 #endif
+#ifndef RG_FQC_CTAS
+#define RG_FQC_CTAS 4         // phase-only class, fidelity role.  Measured on B200 (C4, 8192 x 1000): 4 CTAs/SM (128 registers, 8 B of
+                              // spills) 0.193 ms, 5 CTAs 0.200, 6 CTAs (80 registers, 240 B) 0.258, 8 CTAs 0.417; 7-level model 0.274 / 0.350 / 0.515
+#endif
+#ifndef RG_FQC_ERR_CTAS
+#define RG_FQC_ERR_CTAS 3     // phase-only class, error role: 3 CTAs/SM (168 registers) 0.334 ms, 4 (128) 0.357, 2 (192) 0.390, 5 0.480
+#endif
 
 // ERR = false: fidelity role.   Fout[b] = F (fmode 0) or 1 - F (fmode 1);  out[b*nx + ...] = scale0 * dF/dx  (x_add target part * scale0T)
 // ERR = true : role of error source e = blockIdx.y.  Fout[b*ne + e] = F_d2err[e];  out[(b*ne+e)*nx + ...] = dF_d2err[e]/dx
-template <int D, unsigned UMASK, bool ERR, bool DA>
-__global__ void __launch_bounds__(128, ERR ? 2 : RG_FQ_CTAS)
-k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
+// PC = true: phase-only drive class (constants from k_fqc_consts in P.pc_consts, one sincos per step and sweep).
+template <int D, unsigned UMASK, bool ERR, bool DA, bool PC = false>
+__global__ void __launch_bounds__(128, PC ? (ERR ? RG_FQC_ERR_CTAS : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
+k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
           int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int* __restrict__ status) {
     constexpr int NB = b2_nblocks(D, UMASK);
     constexpr int DD = D * D;
     typedef FQLayout<D, UMASK> LY;
     typedef QS<NB> Q;
     extern __shared__ cplx smem[];
-    const StagedPlan sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    StagedPlan sp{};
+    if constexpr (!PC) sp = stage_plan(P, tp, reinterpret_cast<unsigned char*>(smem));
+    const size_t plan_cplx = PC ? 0 : staged_plan_bytes(P.nterms, tp.nent, D) / sizeof(cplx);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ppc = 4 / wpp;                                     // pulses per CTA
     const int pslot = warp / wpp, wip = warp - pslot * wpp;      // pulse slot in the CTA, warp within the pulse
@@ -274,7 +459,7 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     const int t = wip * 32 + lane;                               // lane within the pulse = chunk index
     const int es = ERR ? (int)blockIdx.y : 0;
     const int ne = P.e, nv = P.nvar;
-    cplx* slot = smem + staged_plan_bytes(P.nterms, tp.nent, D) / sizeof(cplx) + (size_t)pslot * LY::slot;
+    cplx* slot = smem + plan_cplx + (size_t)pslot * LY::slot;
     cplx* alg = slot;
     cplx* totQ = slot + LY::alg;                                 // [wpp][2 NB] Q totals, then [wpp][2 NB] V totals
     cplx* totV = totQ + 8 * NB;
@@ -290,7 +475,25 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     // ---- 1. forward sweep over the chunk
     Q q, vq;
     qs_identity(q); qs_zero(vq);
+    QR<NB> r0, r1, r2;                                           // PC: reference propagator, its error differences at eps and eps2
+    if constexpr (PC) {
+        pc_load(r0, P.pc_consts);
+        if constexpr (ERR) { pc_load(r1, P.pc_consts + (size_t)(1 + 2 * es) * 2 * NB); pc_load(r2, P.pc_consts + (size_t)(2 + 2 * es) * 2 * NB); }
+    }
+    const PCArg parg = pc_arg(P);
+    const double* xaddp = xp + (size_t)P.p * P.N;               // PC sweeps read x straight from global memory (no local arrays)
     for (int k = k0; k < k1; ++k) {
+        if constexpr (PC) {
+            const cplx E = pc_phase(P, parg, xp + (size_t)k * P.p, xaddp);
+            QR<NB> u0; pc_rot(u0, r0, E);
+            if constexpr (ERR) {
+                QR<NB> u1; pc_rot(u1, r1, E);
+                Q vn; qr_mul(vn, u0, vq); qr_mul<NB, true>(vn, u1, q);          // V <- U V + D Q_old
+                vq = vn;
+            }
+            Q qn; qr_mul(qn, u0, q); q = qn;
+            continue;
+        }
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
         const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {
@@ -349,7 +552,7 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
             if constexpr (!ERR) {
 #pragma unroll
                 for (int l = 0; l < D; ++l)
-                    if (b2_partner(D, UMASK, l) < 0) mU[l + D * l] = cmk(1.0, 0.0);      // untouched levels: U(l,l) = 1
+                    if (B2P<D, UMASK>::partner(l) < 0) mU[l + D * l] = cmk(1.0, 0.0);      // untouched levels: U(l,l) = 1
             }
 #pragma unroll
             for (int n = 0; n < NB; ++n) {
@@ -486,6 +689,59 @@ k_fused_q(const DevProblem P, const TriPlanDev tp, const double* __restrict__ X,
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
     for (int k = k1 - 1; k >= k0; --k) {
+        if constexpr (PC) {
+            const double* xkp = xp + (size_t)k * P.p;
+            const cplx E = pc_phase(P, parg, xkp, xaddp);
+            QR<NB> u0; pc_rot(u0, r0, E);
+            QR<NB> u1;
+            cplx T1 = cmk(0.0, 0.0), T2 = cmk(0.0, 0.0);
+            if constexpr (!ERR) {
+                Q cp; qr_adjmul(cp, u0, q); q = cp;                                  // C_{k-1} = U_k^dag C_k
+                cplx w[NB]; qr_w(w, g, q);
+#pragma unroll
+                for (int n = 0; n < NB; ++n) cfma(T1, u0.b[n], w[n]);
+            } else {
+                pc_rot(u1, r1, E);
+                {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
+                    Q cp; qr_adjmul(cp, u0, q); q = cp;
+                    Q t1; qr_mul(t1, u1, q);
+                    Q t2; qs_sub(t2, vq, t1);
+                    qr_adjmul(vq, u0, t2);
+                }
+                cplx w[NB]; qr_w(w, h, q); qr_w<NB, true>(w, g, vq);
+                cplx w2[NB]; qr_w(w2, g, q);
+#pragma unroll
+                for (int n = 0; n < NB; ++n) { cfma(T1, u0.b[n], w[n]); cfma(T2, cmul(r2.b[n], E), w2[n]); }
+            }
+            if (parg.v1) {
+                const double val = xkp[parg.vidx];
+                const cplx eta = expm1i(parg.vsc * __dsub_rn(__dadd_rn(val, P.eps), val));
+                double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);
+                if constexpr (!ERR) s *= scale0;
+                else {
+                    const cplx eta2 = expm1i(parg.vsc * __dsub_rn(__dadd_rn(val, P.eps2), val));
+                    s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
+                }
+                if (live) outb[(size_t)P.p * k + parg.vidx] = s;
+            } else for (int v = 0; v < nv; ++v) {
+                const cplx eta = pc_eta(P, xkp, xaddp, v, P.eps);
+                double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);                     // Re tr(G dU C) = -2 Re(eta T1)
+                if constexpr (!ERR) s *= scale0;
+                else {
+                    const cplx eta2 = pc_eta(P, xkp, xaddp, v, P.eps2);
+                    s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
+                }
+                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
+                else acc[P.var_index[v]] += s;
+            }
+            if constexpr (!ERR) { Q gn; qr_rmul(gn, g, u0); g = gn; }                // G_{k-1} = G_k U_k
+            else {                                                                   // H' <- H' U + G' D ;  G' <- G' U
+                Q hn; qr_rmul(hn, h, u0); qr_rmul<NB, true>(hn, g, u1);
+                Q gn; qr_rmul(gn, g, u0);
+                h = hn; g = gn;
+            }
+            continue;
+        }
         for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
         const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {

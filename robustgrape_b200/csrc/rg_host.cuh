@@ -90,6 +90,7 @@ struct rg_problem {
     int force_dense_alg = 0;      // RG_DENSE_ALG=1: dense fidelity algebra even then (A/B and tests)
     int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
     int fq_ctas[2] = {0, 0};      // resident CTAs/SM of k_fused_q (fidelity role, error role)
+    int pc_ready = 0;             // phase-only class: constants evaluated (k_fqc_consts); dp.pc is cleared if they are out of range
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;
     double tri_density = 1.0;
@@ -127,6 +128,7 @@ void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas);
 int rg_fq_pattern(const rg_problem* pr);
 int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
                  double scale0, double scale0T, int do_grad);
+int rg_fq_prepare(rg_problem* pr);
 static inline bool rg_use_b2(const rg_problem* pr) {
     return !pr->force_group && !pr->force_dense && !pr->force_group_sweeps && !pr->fused_agg && rg_b2_pattern(pr) != 0;
 }

@@ -71,6 +71,33 @@ def detuned_problem(ntimes, t0, errors=("amp",)):
     return rg.FidelityRobustGRAPEProblem(up, PROJ5, rt.cz_target("symmetric_blockaded"))
 
 
+def phase_only_problem(ntimes, t0, model="symmetric_blockaded", nerr=2, nparam=1):
+    """A member of the phase-only drive class (DevProblem::pc) that is *not* the plain CZ problem: the laser phase is
+    0.7 * x[nparam-1] + 0.3 plus a per-pulse offset 1.3 * x_add[1] (two EXPI factors, one of them in an additional parameter),
+    the coupling constants are complex, and there are a multiplicative (1 + e) and a linear (e) amplitude-type error source with
+    different complex strengths per block.  nparam = 2 adds a control the Hamiltonian does not depend on (zero gradient rows)."""
+    d = 5 if model == "symmetric_blockaded" else 7
+    up_ent = rt._SYM_UP if d == 5 else rt._FB_UP
+    ph = (Factor.expi(S_MAIN, nparam - 1, -0.7, 0.3), Factor.expi(S_ADD, 1, 1.3, 0.0))
+    phc = (Factor.expi(S_MAIN, nparam - 1, 0.7, -0.3), Factor.expi(S_ADD, 1, -1.3, 0.0))        # conjugate phase of the lower triangle
+    c0 = [0.5 + 0.1j, 0.6 - 0.2j, 0.4 + 0.3j]
+    c1 = [0.2 - 0.1j, 0.1 + 0.25j, -0.3 + 0.1j]
+
+    def pair(coefs, extra, owner):
+        up_t = tuple((r, c, v * coefs[i]) for i, (r, c, v) in enumerate(up_ent))
+        dn_t = tuple((c, r, np.conj(v * coefs[i])) for i, (r, c, v) in enumerate(up_ent))
+        return [Term(1.0, ph + extra, up_t, owner), Term(1.0, phc + extra, dn_t, owner)]
+
+    terms = pair(c0, (), OWNER_H0)
+    srcs = []
+    if nerr >= 1:
+        srcs.append(rg.ErrorSource(TermErrorHamiltonian(d, pair(c0, (Factor.err1p_m1(),), 0))))
+    if nerr >= 2:
+        srcs.append(rg.ErrorSource(TermErrorHamiltonian(d, pair(c1, (Factor.err(),), 1))))
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=ntimes, ndim=d, H0=TermHamiltonian(d, terms), nb_additional_param=2, error_sources=srcs)
+    return rg.FidelityRobustGRAPEProblem(up, PROJ5 if d == 5 else PROJ7, rt.cz_target(model))
+
+
 def random_pulse(fp, nparam=1, seed=0):
     up = fp.unitary_problem
     rng = np.random.default_rng(seed)

@@ -713,3 +713,57 @@ def test_error_ensemble_on_the_batch_axis(gpu_ctx):
     Fa = rg.calculate_fidelity_and_derivatives_batch(fp, X[:, :2], want_grad=False)[0]
     Fb = rg.calculate_fidelity_and_derivatives_batch(fp, X[:, 2:], want_grad=False)[0]
     assert np.array_equal(np.concatenate([Fa, Fb]), F)
+
+
+def _path(fp, nx):
+    from robustgrape_b200.unitary_calculations import device_problem
+    return device_problem(fp).path(nx)
+
+
+@pytest.mark.parametrize("model,N,B,nerr,nparam", [("symmetric_blockaded", 77, 5, 2, 1), ("full_blockaded", 40, 3, 2, 1),
+                                                   ("symmetric_blockaded", 33, 9, 1, 2), ("symmetric_blockaded", 200, 2, 0, 1)])
+def test_phase_only_class_equals_generic_fused_kernel(gpu_ctx, monkeypatch, model, N, B, nerr, nparam):
+    """Phase-only drive class (k_fused_q PC instantiation: step constants evaluated once, own sincos) against the generic
+    closed-form kernel (RG_NO_PC=1) on a problem with a two-factor phase, complex couplings and two kinds of amplitude error, and
+    both against the exact-semantics oracle for one pulse."""
+    from cases import phase_only_problem
+    from oracle import exact_oracle as eo
+    fp = phase_only_problem(N, 7.613 * N / 1000 * 6, model, nerr, nparam)
+    X = 2 * np.pi * np.random.default_rng(N + B).random((nparam * N + 2, B)) - np.pi
+    assert _path(fp, X.shape[0]) == "fused_q_pc"
+    new = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    monkeypatch.setenv("RG_NO_PC", "1")
+    fp2 = phase_only_problem(N, 7.613 * N / 1000 * 6, model, nerr, nparam)
+    assert _path(fp2, X.shape[0]) == "fused_q"
+    old = rg.calculate_fidelity_and_derivatives_batch(fp2, X)
+    for k, u, v in zip(NAMES, new, old):
+        assert relmax(u, v) < 1e-12, (k, relmax(u, v))
+    if N <= 80:
+        ex = eo.calculate_fidelity_and_derivatives(fp, X[:, 0])
+        for k, g, e in zip(NAMES, [np.asarray(a)[..., 0] for a in new], ex):
+            assert relmax(g, e) < 1e-10, (k, relmax(g, e))
+
+
+def test_phase_only_class_detection(gpu_ctx):
+    """The class is a property of the term lists: the CZ problems of BASELINE configs 1, 2, 4 are in it, a detuned or
+    amplitude-controlled Hamiltonian is not, and a step norm outside the closed-form range falls back to the generic kernel."""
+    assert _path(cz_problem(50, 7.613, ("amp",)), 51) == "fused_q_pc"
+    assert _path(cz_problem(50, 7.613, ("amp",), "full_blockaded"), 51) == "fused_q_pc"
+    assert _path(cz_problem(50, 7.613, ("amp", "freq")), 51) == "block2"
+    assert _path(cz_problem(50, 7.613, (), delta=0.3), 51) == "block2"
+    assert _path(detuned_problem(50, 7.613), 102) != "fused_q_pc"
+    assert _path(cz_problem(4, 4 * 9.0, ("amp",)), 5) == "fused_q"          # z > 4.5: constants out of range
+
+
+def test_phase_only_large_arguments(gpu_ctx):
+    """Phases far outside [-pi, pi] (|x| up to 3e5: the Cody-Waite reduction up to 1e5, the library sincos beyond) against the
+    literal restatement's F and the generic kernel."""
+    fp = cz_problem(40, 7.613 * 40 / 1000 * 5)
+    rng = np.random.default_rng(5)
+    X = np.concatenate([rng.uniform(-3e5, 3e5, (40, 6)), rng.uniform(-3, 3, (1, 6))])
+    X[:, :3] *= 1e-2
+    F, Fdx, _, _ = rg.calculate_fidelity_and_derivatives_batch(fp, X)
+    for b in range(6):
+        a = ro.calculate_fidelity_and_derivatives(fp, X[:, b])
+        assert abs(F[b] - a[0]) < 1e-10, (b, F[b], a[0])
+        assert relmax(Fdx[:, b], a[1]) < 2e-5
