@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "librobustgrape_b200.so"
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-                 "-diag-suppress", "68,20058", "-Xcompiler", "-fPIC"]
+                 "-diag-suppress", "68,128,20058", "-Xcompiler", "-fPIC"]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 OBJ_DIR = ROOT / "lib" / "obj"
 

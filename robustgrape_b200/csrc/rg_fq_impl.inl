@@ -26,7 +26,7 @@ int prepare_fq(rg_problem* pr) {
     if (hflag) pr->dp.pc = 0;          // out of the closed-form range: the generic kernel runs and reports it
     else pr->dp.pc_consts = static_cast<const cplx*>(buf);
     pr->pc_ready = 1;
-    pr->fq_ctas[0] = 0;
+    pr->fq_ready = 0;
     return RG_OK;
 }
 int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
@@ -37,38 +37,47 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     const bool pc = pr->dp.pc != 0;
     DevProblem Pl = P;
     Pl.pc = pr->dp.pc; Pl.pc_consts = pr->dp.pc_consts;
-    const size_t smem = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc);
     const bool da = pr->diag_alg && !pr->force_dense_alg;
-    if (!pr->fq_ctas[0]) {
-        int rc = set_smem(ctx, k_fused_q<D, UM, false, false, false>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, true, false, false>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, false, true, false>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, true, true, false>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, false, false, true>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, true, false, true>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, false, true, true>, smem); if (rc) return rc;
-        rc = set_smem(ctx, k_fused_q<D, UM, true, true, true>, smem); if (rc) return rc;
-#define RG_FQ_OCC(i, ERRR, DAA, PCC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr->fq_ctas[i], k_fused_q<D, UM, ERRR, DAA, PCC>, 128, smem)
-        if (pc) { if (da) { RG_FQ_OCC(0, false, true, true); RG_FQ_OCC(1, true, true, true); } else { RG_FQ_OCC(0, false, false, true); RG_FQ_OCC(1, true, false, true); } }
-        else { if (da) { RG_FQ_OCC(0, false, true, false); RG_FQ_OCC(1, true, true, false); } else { RG_FQ_OCC(0, false, false, false); RG_FQ_OCC(1, true, false, false); } }
-#undef RG_FQ_OCC
-        pr->fq_ctas[0] = std::max(1, pr->fq_ctas[0]); pr->fq_ctas[1] = std::max(1, pr->fq_ctas[1]);
+    const int role = err_role ? 1 : 0;
+    // Per warps-per-pulse choice w: chunk length, shared memory (the staged controls need (N p + 32 w) doubles per pulse; a pulse
+    // that does not fit is read from global memory instead) and resident CTAs/SM from the occupancy query -- all fixed per problem.
+    if (!pr->fq_ready) {
+        for (int wi = 0; wi < 3; ++wi) {
+            const int w = 1 << wi, Lw = (P.N + 32 * w - 1) / (32 * w);
+            bool xs = pr->stage_xs != 0;
+            size_t sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, xs);
+            if (sm > 200 * 1024) { xs = false; sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, xs); }
+            pr->fq_xs[wi] = xs ? 1 : 0; pr->fq_smem[wi] = sm;
+            for (int r = 0; r < 2; ++r) {
+                int occ = 1, rc = RG_OK;
+#define RG_FQ_SET(ERRR, DAA, PCC) { rc = set_smem(ctx, k_fused_q<D, UM, ERRR, DAA, PCC>, sm); if (!rc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_q<D, UM, ERRR, DAA, PCC>, 128, sm); }
+                if (pc) { if (r) { if (da) RG_FQ_SET(true, true, true) else RG_FQ_SET(true, false, true) } else { if (da) RG_FQ_SET(false, true, true) else RG_FQ_SET(false, false, true) } }
+                else { if (r) { if (da) RG_FQ_SET(true, true, false) else RG_FQ_SET(true, false, false) } else { if (da) RG_FQ_SET(false, true, false) else RG_FQ_SET(false, false, false) } }
+#undef RG_FQ_SET
+                if (rc) return rc;
+                pr->fq_occ[r][wi] = std::max(1, occ);
+            }
+        }
+        pr->fq_ready = 1;
     }
     // warps per pulse: cost = waves * (sweep steps per lane + fixed scan/algebra overhead of ~24 sweep steps)
-    const double cap = (double)ctx->sm_count * pr->fq_ctas[err_role ? 1 : 0];
-    int wpp = 1; double best = 1e300;
-    for (int w = 1; w <= 4; w <<= 1) {
+    int wpp = 1, wsel = 0; double best = 1e300;
+    for (int wi = 0; wi < 3; ++wi) {
+        const int w = 1 << wi;
         const int Lw = (P.N + 32 * w - 1) / (32 * w);
+        const double cap = (double)ctx->sm_count * pr->fq_occ[role][wi];
         const double ctas = std::ceil((double)B * w / 4.0) * (err_role ? P.e : 1);
         const double cost = std::ceil(ctas / cap) * (Lw + 24.0);
-        if (cost < best) { best = cost; wpp = w; }
+        if (cost < best) { best = cost; wpp = w; wsel = wi; }
     }
-    if (pr->wpp_override > 0) wpp = pr->wpp_override >= 4 ? 4 : (pr->wpp_override >= 2 ? 2 : 1);
+    if (pr->wpp_override > 0) { wpp = pr->wpp_override >= 4 ? 4 : (pr->wpp_override >= 2 ? 2 : 1); wsel = wpp == 4 ? 2 : (wpp == 2 ? 1 : 0); }
     const int L = (P.N + 32 * wpp - 1) / (32 * wpp);
     const int ppc = 4 / wpp;
+    const size_t smem = pr->fq_smem[wsel];
+    const int use_xs = pr->fq_xs[wsel];
     dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? P.e : 1);
     KTimer kt(ctx, err_role ? RG_K_GRAD_ERR : RG_K_GRAD);
-#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, ctx->d_status)
+#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, use_xs, ctx->d_status)
     if (pc) {
         if (err_role) { if (da) RG_FQ_GO(true, true, true); else RG_FQ_GO(true, false, true); }
         else { if (da) RG_FQ_GO(false, true, true); else RG_FQ_GO(false, false, true); }

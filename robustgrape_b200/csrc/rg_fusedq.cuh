@@ -220,8 +220,7 @@ __constant__ double c_sc[16] = {
     -1.38888888888741095749e-03, 4.16666666666666019037e-02};                                                      // C6 .. C1
 static __device__ __noinline__ double2 rg_sincos_slow(double x) { double2 r; sincos(x, &r.y, &r.x); return r; }
 // (coefficients come from the constant bank as DFMA operands: as literals each one costs a UMOV pair per use)
-__device__ __forceinline__ void rg_sincos(double x, double& s, double& c) {
-    if (fabs(x) > 1.0e5) { const double2 r = rg_sincos_slow(x); s = r.y; c = r.x; return; }
+__device__ __forceinline__ void rg_sincos_core(double x, double& s, double& c) {      // branch-free; valid for |x| <= 1e5
     const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: the fma rounds x * 2/pi to the nearest integer
     const double t = fma(x, c_sc[0], MAGIC);
     const int q = __double2loint(t);
@@ -240,6 +239,15 @@ __device__ __forceinline__ void rg_sincos(double x, double& s, double& c) {
     // sign flips on the high words: s negative in quadrants 2, 3; c negative in quadrants 1, 2
     s = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
     c = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
+}
+__device__ __forceinline__ void rg_sincos(double x, double& s, double& c) {
+    if (fabs(x) > 1.0e5) { const double2 r = rg_sincos_slow(x); s = r.y; c = r.x; return; }
+    rg_sincos_core(x, s, c);
+}
+// e^{ih} - 1 by its series, branch-free; valid for |h| < 1e-3 (truncation below 2e-22 relative)
+__device__ __forceinline__ cplx expm1i_small(double h) {
+    const double h2 = h * h;
+    return cmk(-0.5 * h2 * (1.0 - h2 * (1.0 / 12.0) * (1.0 - h2 * (1.0 / 30.0))), h * (1.0 - h2 * (1.0 / 6.0) * (1.0 - h2 * (1.0 / 20.0))));
 }
 // E_k = prod_f exp(i (scale_f v_f + offset_f)); the common case (one factor in a main parameter) is hoisted into PCArg
 struct PCArg { int fast, idx, plain; double sc, of; int v1, vidx; double vsc; };
@@ -264,12 +272,11 @@ static __device__ __noinline__ void pc_phase_general(const DevProblem& P, const 
     }
     *Eout = E;
 }
-__device__ __forceinline__ cplx pc_phase(const DevProblem& P, const PCArg& a, const double* xk, const double* xadd) {
+// v = xk[a.idx], loaded by the caller one step ahead of its use (the sweeps are latency bound: one warp's steps are a serial chain)
+__device__ __forceinline__ cplx pc_phase(const DevProblem& P, const PCArg& a, const double* xk, const double* xadd, double v) {
     cplx E;
-    if (a.fast) {
-        const double v = xk[a.idx];
-        rg_sincos(a.plain ? v : fma(a.sc, v, a.of), E.y, E.x);
-    } else pc_phase_general(P, xk, xadd, &E);
+    if (a.fast) rg_sincos(a.plain ? v : fma(a.sc, v, a.of), E.y, E.x);
+    else pc_phase_general(P, xk, xadd, &E);
     return E;
 }
 // e^{i sigma_v h} - 1 with h = fl(val + e) - val the step actually taken in variable v (src/UnitaryCalculations.jl:50)
@@ -293,7 +300,7 @@ __global__ void k_fqc_consts(const DevProblem P, const TriPlanDev tp, cplx* __re
     for (int i = 0; i < RG_MAX_MAIN; ++i) xk[i] = 0.0;
     for (int i = 0; i < RG_MAX_ADD; ++i) xadd[i] = 0.0;
     const TrigSlots tr{0, 0.0, 1.0, 0.0, 1.0};
-    const cplx Er = cconj(pc_phase(P, pc_arg(P), xk, xadd));
+    const cplx Er = cconj(pc_phase(P, pc_arg(P), xk, xadd, 0.0));
     int Kmax = 0;
     {
         QS<NB> u[1];
@@ -325,20 +332,151 @@ template <int NB> __device__ __forceinline__ void pc_rot(QR<NB>& u, const QR<NB>
     for (int n = 0; n < NB; ++n) { u.a[n] = ref.a[n]; u.b[n] = cmul(ref.b[n], E); }
 }
 
-// shared-memory slot of one pulse (in complex numbers)
-template <int D, unsigned UMASK> struct FQLayout {
-    static constexpr int NB = b2_nblocks(D, UMASK);
-    static constexpr int DD = D * D;
-    static constexpr int alg = 14 * DD + D + 1;             // fid_algebra scratch
-    static constexpr int tot = 4 * 4 * NB;                  // per warp of the pulse: inclusive totals (Q, V): 2 * 2 * NB, padded
-    static constexpr int fin = 4 * NB;                      // C_N, W_N
-    static constexpr int acc = 4 * RG_MAX_ADD;              // per warp x_add partial sums (as doubles: 4 warps x RG_MAX_ADD -> /2 cplx) + addT
-    static constexpr int slot = alg + tot + fin + acc + 1;
-};
-__host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int nent, bool pc = false) {
+// ---- sweeps of the phase-only class --------------------------------------------------------------------------------------
+// SPECIAL = the common shape (one EXPI factor in a main parameter, which is also the only perturbation variable: the CZ problems
+// of BASELINE.json configs 1, 2, 4): the loop body is one basic block -- the control of step k+2 is loaded and the phase factor of
+// step k+1 is evaluated while the quaternion products of step k run, so the scheduler interleaves the two dependency chains (one
+// warp's steps are a serial chain and only 3-4 warps per scheduler are resident); rare cases (|x| > 1e5, finite-difference steps
+// beyond the series range) are patched by branches at the end of the block.  Otherwise the general per-factor / per-variable loops.
+#ifndef RG_PC_UNROLL
+#define RG_PC_UNROLL 1
+#endif
+constexpr int kPcUnroll = RG_PC_UNROLL;
+template <int NB, bool ERR, bool SPECIAL>
+__device__ __forceinline__ void pc_forward(const DevProblem& P, const PCArg& a, const double* __restrict__ xrow, const double* xaddp,
+                                           int k0, int k1, const QR<NB>& r0, const QR<NB>& r1, QS<NB>& q, QS<NB>& vq) {
+    if (k0 >= k1) return;
+    const size_t p = (size_t)P.p;
+    double xa = 0.0, xb = 0.0;
+    cplx En = cmk(1.0, 0.0);
+    if constexpr (SPECIAL) {
+        xa = xrow[k0 * p + a.idx];
+        xb = xrow[min(k0 + 1, k1 - 1) * p + a.idx];
+        rg_sincos(a.plain ? xa : fma(a.sc, xa, a.of), En.y, En.x);
+    }
+#pragma unroll kPcUnroll
+    for (int k = k0; k < k1; ++k) {
+        cplx E;
+        double un = 0.0;
+        if constexpr (SPECIAL) {
+            E = En;
+            xa = xb;
+            xb = xrow[min(k + 2, k1 - 1) * p + a.idx];
+            un = a.plain ? xa : fma(a.sc, xa, a.of);
+            rg_sincos_core(un, En.y, En.x);
+        } else E = pc_phase(P, a, xrow + k * p, xaddp, xrow[k * p + a.idx]);
+        QR<NB> u0; pc_rot(u0, r0, E);
+        if constexpr (ERR) {
+            QR<NB> u1; pc_rot(u1, r1, E);
+            QS<NB> vn; qr_mul(vn, u0, vq); qr_mul<NB, true>(vn, u1, q);          // V <- U V + D Q_old
+            vq = vn;
+        }
+        QS<NB> qn; qr_mul(qn, u0, q); q = qn;
+        if constexpr (SPECIAL) { if (fabs(un) > 1.0e5) { const double2 r = rg_sincos_slow(un); En = cmk(r.x, r.y); } }
+    }
+}
+// backward sweep: rewinds (q, vq), advances the co-states (g, h), emits one gradient entry per perturbation variable and step
+template <int NB, bool ERR, bool SPECIAL, class PUT>
+__device__ __forceinline__ void pc_backward(const DevProblem& P, const PCArg& a, const double* __restrict__ xrow, const double* xaddp,
+                                            int k0, int k1, const QR<NB>& r0, const QR<NB>& r1, const QR<NB>& r2, QS<NB>& q, QS<NB>& vq,
+                                            QS<NB>& g, QS<NB>& h, double scale0, double f1, double f2, double* acc, PUT put_grad) {
+    if (k0 >= k1) return;
+    const size_t p = (size_t)P.p;
+    const int nv = P.nvar;
+    double xa = 0.0, xb = 0.0;
+    cplx En = cmk(1.0, 0.0);
+    if constexpr (SPECIAL) {
+        xa = xrow[(k1 - 1) * p + a.idx];
+        xb = xrow[max(k1 - 2, k0) * p + a.idx];
+        rg_sincos(a.plain ? xa : fma(a.sc, xa, a.of), En.y, En.x);
+    }
+#pragma unroll kPcUnroll
+    for (int k = k1 - 1; k >= k0; --k) {
+        cplx E;
+        double un = 0.0, xcur = 0.0;
+        if constexpr (SPECIAL) {
+            E = En; xcur = xa;
+            xa = xb;
+            xb = xrow[max(k - 2, k0) * p + a.idx];
+            un = a.plain ? xa : fma(a.sc, xa, a.of);
+            rg_sincos_core(un, En.y, En.x);
+        } else E = pc_phase(P, a, xrow + k * p, xaddp, xrow[k * p + a.idx]);
+        QR<NB> u0; pc_rot(u0, r0, E);
+        QR<NB> u1;
+        cplx T1 = cmk(0.0, 0.0), T2 = cmk(0.0, 0.0);
+        if constexpr (!ERR) {
+            QS<NB> cp; qr_adjmul(cp, u0, q); q = cp;                                  // C_{k-1} = U_k^dag C_k
+            cplx w[NB]; qr_w(w, g, q);
+#pragma unroll
+            for (int n = 0; n < NB; ++n) cfma(T1, u0.b[n], w[n]);
+        } else {
+            pc_rot(u1, r1, E);
+            {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
+                QS<NB> cp; qr_adjmul(cp, u0, q); q = cp;
+                QS<NB> t1; qr_mul(t1, u1, q);
+                QS<NB> t2; qs_sub(t2, vq, t1);
+                qr_adjmul(vq, u0, t2);
+            }
+            cplx w[NB]; qr_w(w, h, q); qr_w<NB, true>(w, g, vq);
+            cplx w2[NB]; qr_w(w2, g, q);
+#pragma unroll
+            for (int n = 0; n < NB; ++n) { cfma(T1, u0.b[n], w[n]); cfma(T2, cmul(r2.b[n], E), w2[n]); }
+        }
+        if constexpr (SPECIAL) {
+            // Re tr(G dU C) = -2 Re(eta T1), eta = e^{i sigma h} - 1, h = fl(x + eps) - x the step actually taken (:50)
+            const double h1 = a.vsc * __dsub_rn(__dadd_rn(xcur, P.eps), xcur);
+            cplx eta = expm1i_small(h1);
+            if (fabs(h1) >= 1e-3) expm1i_large(h1, &eta);
+            double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);
+            if constexpr (!ERR) s *= scale0;
+            else {
+                const double h2 = a.vsc * __dsub_rn(__dadd_rn(xcur, P.eps2), xcur);
+                cplx eta2 = expm1i_small(h2);
+                if (fabs(h2) >= 1e-3) expm1i_large(h2, &eta2);
+                s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
+            }
+            put_grad(k, a.vidx, s);
+        } else {
+            const double* xkp = xrow + k * p;
+            for (int v = 0; v < nv; ++v) {
+                const cplx eta = pc_eta(P, xkp, xaddp, v, P.eps);
+                double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);
+                if constexpr (!ERR) s *= scale0;
+                else {
+                    const cplx eta2 = pc_eta(P, xkp, xaddp, v, P.eps2);
+                    s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
+                }
+                if (P.var_space[v] == RG_S_MAIN) put_grad(k, P.var_index[v], s);
+                else acc[P.var_index[v]] += s;
+            }
+        }
+        if constexpr (!ERR) { QS<NB> gn; qr_rmul(gn, g, u0); g = gn; }                // G_{k-1} = G_k U_k
+        else {                                                                       // H' <- H' U + G' D ;  G' <- G' U
+            QS<NB> hn; qr_rmul(hn, h, u0); qr_rmul<NB, true>(hn, g, u1);
+            QS<NB> gn; qr_rmul(gn, g, u0);
+            h = hn; g = gn;
+        }
+        if constexpr (SPECIAL) { if (fabs(un) > 1.0e5) { const double2 r = rg_sincos_slow(un); En = cmk(r.x, r.y); } }
+    }
+}
+
+// Shared-memory slot of one pulse (in complex numbers): fidelity-algebra scratch | per-warp scan totals | C_N, W_N | x_add partial
+// sums | the pulse's controls.  The controls are staged once, coalesced, as one row per lane (= chunk of L steps) with an odd row
+// stride so that lanes reading their own step hit distinct banks; both sweeps read them from there (the lane-strided global loads
+// were the top stall of the phase-only kernels: long_scoreboard 2.7 cycles per issue), and the backward sweep overwrites x_k with
+// the gradient entry of step k, so the gradient also leaves with coalesced stores.
+struct FQSlot { int alg, tot, fin, acc, xs, slot, S; };       // offsets in cplx of each part, total, row stride of xs in doubles
+__host__ __device__ inline FQSlot fq_slot(int d, int nb, bool da, int a, int p, int wpp, int L, bool use_xs) {
     const int DD = d * d;
-    const size_t slot = (size_t)(14 * DD + d + 1) + 16 * nb + 4 * nb + 4 * RG_MAX_ADD + 1;
-    return (pc ? 0 : staged_plan_bytes(nterms, nent, d)) + 4 * slot * sizeof(cplx);      // the PC kernels never read the term plan
+    FQSlot f;
+    const int alg = da ? DD * (1 + a) + d * (1 + a) + d / 2 + 1 : 14 * DD + d + 1;
+    f.alg = 0; f.tot = alg; f.fin = f.tot + 16 * nb; f.acc = f.fin + 4 * nb; f.xs = f.acc + 4 * RG_MAX_ADD + 1;
+    f.S = (L * p) | 1;
+    f.slot = f.xs + (use_xs ? (32 * wpp * f.S + 1) / 2 : 0);
+    return f;
+}
+__host__ __device__ inline size_t fq_smem_bytes(int d, int nb, int nterms, int nent, bool pc, bool da, int a, int p, int wpp, int L, bool use_xs) {
+    return (pc ? 0 : staged_plan_bytes(nterms, nent, d)) + (size_t)(4 / wpp) * fq_slot(d, nb, da, a, p, wpp, L, use_xs).slot * sizeof(cplx);
 }
 
 
@@ -441,10 +579,9 @@ struct FQDiag {
 template <int D, unsigned UMASK, bool ERR, bool DA, bool PC = false>
 __global__ void __launch_bounds__(128, PC ? (ERR ? RG_FQC_ERR_CTAS : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
 k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
-          int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int* __restrict__ status) {
+          int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int use_xs, int* __restrict__ status) {
     constexpr int NB = b2_nblocks(D, UMASK);
     constexpr int DD = D * D;
-    typedef FQLayout<D, UMASK> LY;
     typedef QS<NB> Q;
     extern __shared__ cplx smem[];
     StagedPlan sp{};
@@ -459,14 +596,27 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
     const int t = wip * 32 + lane;                               // lane within the pulse = chunk index
     const int es = ERR ? (int)blockIdx.y : 0;
     const int ne = P.e, nv = P.nvar;
-    cplx* slot = smem + plan_cplx + (size_t)pslot * LY::slot;
+    const FQSlot LY = fq_slot(D, NB, DA, P.a, P.p, wpp, L, use_xs != 0);
+    cplx* slot = smem + plan_cplx + (size_t)pslot * LY.slot;
     cplx* alg = slot;
-    cplx* totQ = slot + LY::alg;                                 // [wpp][2 NB] Q totals, then [wpp][2 NB] V totals
+    cplx* totQ = slot + LY.tot;                                  // [wpp][2 NB] Q totals, then [wpp][2 NB] V totals
     cplx* totV = totQ + 8 * NB;
-    cplx* finC = slot + LY::alg + LY::tot;                       // C_N (2 NB), W_N (2 NB)
-    double* accS = reinterpret_cast<double*>(slot + LY::alg + LY::tot + LY::fin);      // [4][RG_MAX_ADD] partial sums, then addT [RG_MAX_ADD]
+    cplx* finC = slot + LY.fin;                                  // C_N (2 NB), W_N (2 NB)
+    double* accS = reinterpret_cast<double*>(slot + LY.acc);     // [4][RG_MAX_ADD] partial sums, then addT [RG_MAX_ADD]
     double* addT = accS + 4 * RG_MAX_ADD;
+    double* xs = reinterpret_cast<double*>(slot + LY.xs);        // [32 wpp][S] staged controls, later the gradient
     const double* xp = X + (size_t)b * P.nx;
+    const int Lp = L * P.p;
+    if (use_xs) {
+        // row r of the pulse = steps [rL, (r+1)L): warp wip takes rows wip, wip + wpp, ...; lanes run along the row (coalesced)
+        for (int r = wip; r < 32 * wpp; r += wpp) {
+            const int n = min(Lp, P.p * P.N - r * Lp);
+            for (int c = lane; c < n; c += 32) xs[r * LY.S + c] = xp[(size_t)r * Lp + c];
+        }
+        __syncthreads();
+    }
+    // controls of step k of this lane's chunk: shared row t (or global memory when the pulse does not fit)
+    const double* xrow = use_xs ? xs + (size_t)t * LY.S - (size_t)min(P.N, t * L) * P.p : xp;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     const int k0 = min(P.N, t * L), k1 = min(P.N, k0 + L);
@@ -481,20 +631,14 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
         if constexpr (ERR) { pc_load(r1, P.pc_consts + (size_t)(1 + 2 * es) * 2 * NB); pc_load(r2, P.pc_consts + (size_t)(2 + 2 * es) * 2 * NB); }
     }
     const PCArg parg = pc_arg(P);
-    const double* xaddp = xp + (size_t)P.p * P.N;               // PC sweeps read x straight from global memory (no local arrays)
-    for (int k = k0; k < k1; ++k) {
-        if constexpr (PC) {
-            const cplx E = pc_phase(P, parg, xp + (size_t)k * P.p, xaddp);
-            QR<NB> u0; pc_rot(u0, r0, E);
-            if constexpr (ERR) {
-                QR<NB> u1; pc_rot(u1, r1, E);
-                Q vn; qr_mul(vn, u0, vq); qr_mul<NB, true>(vn, u1, q);          // V <- U V + D Q_old
-                vq = vn;
-            }
-            Q qn; qr_mul(qn, u0, q); q = qn;
-            continue;
-        }
-        for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    const double* xaddp = xp + (size_t)P.p * P.N;               // PC sweeps read x_add through this pointer (no local arrays)
+    const bool pc_special = PC && parg.fast && parg.v1 && parg.vidx == parg.idx;
+    if constexpr (PC) {
+        if (pc_special) pc_forward<NB, ERR, true>(P, parg, xrow, xaddp, k0, k1, r0, r1, q, vq);
+        else pc_forward<NB, ERR, false>(P, parg, xrow, xaddp, k0, k1, r0, r1, q, vq);
+    }
+    for (int k = PC ? k1 : k0; k < k1; ++k) {
+        for (int i = 0; i < P.p; ++i) xk[i] = xrow[(size_t)k * P.p + i];
         const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {
             Q u[1];
@@ -566,9 +710,9 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
     // diagonal algebra: the first warp evaluates the target diagonal u0(x_add) and its finite differences in x_add
     cplx* tcs = alg;                                   // [ntt]               term coefficients
     cplx* dtc = alg + DD;                              // [a][ntt]            their differences / eps
-    cplx* u0s = alg + DD * (1 + RG_MAX_ADD);           // [D]
+    cplx* u0s = alg + DD * (1 + P.a);                  // [D]
     cplx* v0s = u0s + D;                               // [a][D]
-    double* pws = reinterpret_cast<double*>(v0s + RG_MAX_ADD * D);      // [D] projector diagonal
+    double* pws = reinterpret_cast<double*>(v0s + P.a * D);             // [D] projector diagonal
     if constexpr (DA) {
         if (wip == 0) {
             EvalCtx ec{nullptr, xadd, 0.0, P.table, P.N, 0};
@@ -686,63 +830,17 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
 #pragma unroll
     for (int j = 0; j < RG_MAX_ADD; ++j) acc[j] = 0.0;
     double* outb = ERR ? out + ((size_t)b * ne + es) * P.nx : out + (size_t)b * P.nx;
+    double* grow = use_xs ? const_cast<double*>(xrow) : outb;          // gradient entry of step k replaces x_k in the staged row
+    const bool gput = use_xs || live;
+    auto put_grad = [&](int k, int idx, double s) { if (gput) grow[(size_t)P.p * k + idx] = s; };
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
-    for (int k = k1 - 1; k >= k0; --k) {
-        if constexpr (PC) {
-            const double* xkp = xp + (size_t)k * P.p;
-            const cplx E = pc_phase(P, parg, xkp, xaddp);
-            QR<NB> u0; pc_rot(u0, r0, E);
-            QR<NB> u1;
-            cplx T1 = cmk(0.0, 0.0), T2 = cmk(0.0, 0.0);
-            if constexpr (!ERR) {
-                Q cp; qr_adjmul(cp, u0, q); q = cp;                                  // C_{k-1} = U_k^dag C_k
-                cplx w[NB]; qr_w(w, g, q);
-#pragma unroll
-                for (int n = 0; n < NB; ++n) cfma(T1, u0.b[n], w[n]);
-            } else {
-                pc_rot(u1, r1, E);
-                {   // rewind: C_{k-1} = U^dag C_k ;  W_{k-1} = U^dag (W_k - D_k C_{k-1})
-                    Q cp; qr_adjmul(cp, u0, q); q = cp;
-                    Q t1; qr_mul(t1, u1, q);
-                    Q t2; qs_sub(t2, vq, t1);
-                    qr_adjmul(vq, u0, t2);
-                }
-                cplx w[NB]; qr_w(w, h, q); qr_w<NB, true>(w, g, vq);
-                cplx w2[NB]; qr_w(w2, g, q);
-#pragma unroll
-                for (int n = 0; n < NB; ++n) { cfma(T1, u0.b[n], w[n]); cfma(T2, cmul(r2.b[n], E), w2[n]); }
-            }
-            if (parg.v1) {
-                const double val = xkp[parg.vidx];
-                const cplx eta = expm1i(parg.vsc * __dsub_rn(__dadd_rn(val, P.eps), val));
-                double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);
-                if constexpr (!ERR) s *= scale0;
-                else {
-                    const cplx eta2 = expm1i(parg.vsc * __dsub_rn(__dadd_rn(val, P.eps2), val));
-                    s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
-                }
-                if (live) outb[(size_t)P.p * k + parg.vidx] = s;
-            } else for (int v = 0; v < nv; ++v) {
-                const cplx eta = pc_eta(P, xkp, xaddp, v, P.eps);
-                double s = -2.0 * (eta.x * T1.x - eta.y * T1.y);                     // Re tr(G dU C) = -2 Re(eta T1)
-                if constexpr (!ERR) s *= scale0;
-                else {
-                    const cplx eta2 = pc_eta(P, xkp, xaddp, v, P.eps2);
-                    s = f1 * s + f2 * (-2.0 * (eta2.x * T2.x - eta2.y * T2.y));
-                }
-                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
-                else acc[P.var_index[v]] += s;
-            }
-            if constexpr (!ERR) { Q gn; qr_rmul(gn, g, u0); g = gn; }                // G_{k-1} = G_k U_k
-            else {                                                                   // H' <- H' U + G' D ;  G' <- G' U
-                Q hn; qr_rmul(hn, h, u0); qr_rmul<NB, true>(hn, g, u1);
-                Q gn; qr_rmul(gn, g, u0);
-                h = hn; g = gn;
-            }
-            continue;
-        }
-        for (int i = 0; i < P.p; ++i) xk[i] = xp[(size_t)k * P.p + i];
+    if constexpr (PC) {
+        if (pc_special) pc_backward<NB, ERR, true>(P, parg, xrow, xaddp, k0, k1, r0, r1, r2, q, vq, g, h, scale0, f1, f2, acc, put_grad);
+        else pc_backward<NB, ERR, false>(P, parg, xrow, xaddp, k0, k1, r0, r1, r2, q, vq, g, h, scale0, f1, f2, acc, put_grad);
+    }
+    for (int k = PC ? k0 - 1 : k1 - 1; k >= k0; --k) {
+        for (int i = 0; i < P.p; ++i) xk[i] = xrow[(size_t)k * P.p + i];
         const TrigSlots tr = trig_eval(P, xk, xadd);
         if constexpr (!ERR) {
             Q u, cp;
@@ -753,7 +851,7 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
                 if (nv == 0) break;
                 Q tt; qs_mul(tt, ud[1], cp);                                         // dU C_{k-1}
                 const double s = qs_retrace(g, tt) * scale0;
-                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
+                if (P.var_space[v] == RG_S_MAIN) put_grad(k, P.var_index[v], s);
                 else acc[P.var_index[v]] += s;
             }
             Q gn; qs_mul(gn, g, u);                                                  // G_{k-1} = G_k U_k
@@ -784,7 +882,7 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
                     s2 = qs_retrace(g, tt);
                 }
                 const double s = f1 * s1 + f2 * s2;
-                if (P.var_space[v] == RG_S_MAIN) { if (live) outb[(size_t)P.p * k + P.var_index[v]] = s; }
+                if (P.var_space[v] == RG_S_MAIN) put_grad(k, P.var_index[v], s);
                 else acc[P.var_index[v]] += s;
             }
             {   // advance: H' <- H' U + G' D ;  G' <- G' U
@@ -793,6 +891,14 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
                 h = hn; g = gn;
             }
         }
+    }
+    if (use_xs) {
+        __syncthreads();                                                   // all rows of the pulse hold gradient entries now
+        if (live)
+            for (int r = wip; r < 32 * wpp; r += wpp) {
+                const int n = min(Lp, P.p * P.N - r * Lp);
+                for (int c = lane; c < n; c += 32) outb[(size_t)r * Lp + c] = xs[r * LY.S + c];
+            }
     }
     // ---- x_add entries: fixed-order reduction over the pulse's lanes, plus the target-derivative part from the algebra
     if (P.a > 0) {

@@ -89,7 +89,12 @@ struct rg_problem {
     int diag_alg = 0;             // projector and target are diagonal: elementwise fidelity algebra in the fused kernel
     int force_dense_alg = 0;      // RG_DENSE_ALG=1: dense fidelity algebra even then (A/B and tests)
     int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
-    int fq_ctas[2] = {0, 0};      // resident CTAs/SM of k_fused_q (fidelity role, error role)
+    // fused quaternion kernel, per warps-per-pulse choice (1, 2, 4): resident CTAs/SM by role, shared memory, controls staged or not
+    int fq_ready = 0, fq_occ[2][3] = {{1, 1, 1}, {1, 1, 1}}, fq_xs[3] = {0, 0, 0};
+    size_t fq_smem[3] = {0, 0, 0};
+    int stage_xs = 0;             // RG_XS=1: stage the controls (and the gradient) through shared-memory rows.  Measured on B200 and
+                                  // rejected as the default: C4 0.240 ms staged vs 0.183 ms direct (the lane-strided global loads hit L1
+                                  // three times out of four, and staging adds two CTA-wide barriers and a serial load/store phase)
     int pc_ready = 0;             // phase-only class: constants evaluated (k_fqc_consts); dp.pc is cleared if they are out of range
     TriPlanDev tri{};         // upper-triangle assembly plan (Hermitian fast path)
     int tri_ok = 0;

@@ -11,7 +11,7 @@ for src in $root/robustgrape_b200/csrc/*.cu; do
   for tu in "$@"; do
     if [ "$tu" == "$b.cu" ]; then
       use=$out/obj_$name/$b.o
-      nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 68,20058 -Xcompiler -fPIC $flags -c -o $use $src &
+      nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 68,128,20058 -Xcompiler -fPIC $flags -c -o $use $src &
     fi
   done
   objs="$objs $use"
