@@ -695,10 +695,15 @@ def main():
                 fl = json.loads(fp_.read_text())
             except Exception:
                 fl = {}
-        names = {"k_grad": "k_fused_q<5, CZ drive mask, fidelity role> (forward sweep + scan + fidelity algebra + backward sweep, "
-                           "closed-form block propagators recomputed in both sweeps)",
-                 "k_grad_err": "k_fused_q<5, CZ drive mask, error role>", "k_steps": "k_steps_t", "k_chunk_agg": "k_agg_b2", "k_scan": "k_scan"}
-        key = {"k_grad": "k_fused_q_e0", "k_grad_err": "k_fused_q_err"}.get(dom)
+        path = prob.path(nx)                       # which kernel family ran (rg_problem_path)
+        pcs = "_pc" if path == "fused_q_pc" else ""
+        names = {"k_grad": "k_fused_q<5, CZ drive mask, fidelity role" + (", phase-only class" if pcs else "") + "> (forward sweep + scan + "
+                           "fidelity algebra + backward sweep in one launch; " +
+                           ("step constants of the closed-form block propagators evaluated once per problem, one sincos per step and sweep)"
+                            if pcs else "closed-form block propagators recomputed in both sweeps)"),
+                 "k_grad_err": "k_fused_q<5, CZ drive mask, error role" + (", phase-only class" if pcs else "") + ">",
+                 "k_steps": "k_steps_t", "k_chunk_agg": "k_agg_b2", "k_scan": "k_scan"}
+        key = {"k_grad": "k_fused_q" + pcs + "_e0", "k_grad_err": "k_fused_q" + pcs + "_err"}.get(dom)
         per_step = (fl.get(key) or {}).get("fp64_flops_per_pulse_step")
         traffic = (fl.get(key) or {}).get("dram_bytes_per_launch")
         exec_eval = per_step * N if per_step else None
@@ -715,9 +720,10 @@ def main():
             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBps": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak,
                     "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
                     "note": "the fused path touches only x and [cost | grad] in HBM (SURVEY 8d: 16,024 B per pulse); it is FP64/issue bound"},
+            "path": path,
             "note": "workspace-free fused path: one launch per role; the block structure of the Rydberg model is exploited (closed-form "
-                    "2x2 propagators, quaternion state), so executed flops are far below the canonical dense count; dense_fp64 shows "
-                    "the dense-H instantiation of the general kernels on the same workload",
+                    "2x2 propagators, quaternion state, and for phase-only drives step-independent cos/sinc), so executed flops are far "
+                    "below the canonical dense count; dense_fp64 shows the dense-H instantiation of the general kernels on the same workload",
             "fp64": {"achieved_tflops": ach_tf, "peak_dfma_tflops": peak_dfma, "peak_dmma_tflops": peak_dmma},
             "kernel_ms": kernel_ms,
         }

@@ -49,7 +49,7 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     cudaMallocHost(&c->h_status, sizeof(int));
     *c->h_status = 0;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (const char* s = getenv("RG_HOST_SLABS")) c->host_slabs = std::max(1, atoi(s));
+    if (const char* s = getenv("RG_HOST_SLABS")) { c->host_slabs = std::max(1, atoi(s)); c->host_slabs_forced = 1; }
     if (const char* s = getenv("RG_HOST_SLAB_MIN")) c->host_slab_min = std::max(1, atoi(s));
     cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
@@ -69,6 +69,7 @@ extern "C" void rg_ctx_destroy(rg_ctx* c) {
         if (c->s_peer[i]) cudaStreamDestroy(c->s_peer[i]);
         if (c->ev_gather[i]) cudaEventDestroy(c->ev_gather[i]);
     }
+    for (auto& e : c->slab_events) cudaEventDestroy(e);
     if (c->ev_src) cudaEventDestroy(c->ev_src);
     if (c->ev_peer_join) cudaEventDestroy(c->ev_peer_join);
     if (c->d_status) cudaFree(c->d_status);
@@ -498,15 +499,23 @@ extern "C" int rg_cost_and_grad_batch_dev(rg_problem* pr, int32_t B, const doubl
 // H2D of slab i+1 and D2H of slab i-1 overlap the kernels of slab i (full-duplex PCIe), so the
 // end-to-end time approaches max(copy-in, compute, copy-out) instead of their sum.
 struct SlabPipe {
-    rg_ctx* ctx; int nslab, per; std::vector<cudaEvent_t> ev;
-    SlabPipe(rg_ctx* c, int B) : ctx(c) {
-        nslab = std::max(1, std::min(c->host_slabs, B / std::max(1, c->host_slab_min)));
+    rg_ctx* ctx; int nslab, per; std::vector<cudaEvent_t>& ev;
+    // events live in the context and are reused by every call (creating 2 x nslab of them per call cost tens of microseconds
+    // of a ~1.5 ms evaluation)
+    SlabPipe(rg_ctx* c, int B) : ctx(c), ev(c->slab_events) {
+        // fill/drain of the H2D | kernels | D2H pipeline costs 1/nslab of the copy time, every slab a fixed enqueue cost: measured on
+        // B200 (C4, PCIe ceiling 1.49 ms for both directions): 8192 pulses 1.84 ms with 4 slabs, 1.86 with 8, 2.03 with 16; 1024 pulses
+        // 0.36 ms with 1 slab, 0.30 with 4 x 256.  So: about 2048 pulses per slab, at least 4 slabs, none below host_slab_min.
+        const int target = c->host_slabs_forced ? c->host_slabs : std::max(4, std::min(c->host_slabs, B / 2048));
+        nslab = std::max(1, std::min(target, B / std::max(1, c->host_slab_min)));
         per = (B + nslab - 1) / nslab;
         nslab = (B + per - 1) / per;
-        ev.resize(2 * nslab);
-        for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        while ((int)ev.size() < 2 * nslab) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            ev.push_back(e);
+        }
     }
-    ~SlabPipe() { for (auto& e : ev) cudaEventDestroy(e); }
 };
 
 extern "C" int rg_fidelity_and_derivatives_batch(rg_problem* pr, int32_t B, const double* X, double* F, double* F_dx,

@@ -27,8 +27,9 @@ struct rg_ctx {
     size_t ws_limit = (size_t)64 << 30;
     // optional per-kernel timing (CUDA events on the launch stream), see rg_ctx_set_timing
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of the pipelined host entry points
-    int host_slabs = 8;                               // RG_HOST_SLABS (upper bound on the number of slabs)
-    int host_slab_min = 1024;                         // RG_HOST_SLAB_MIN (smallest slab, pulses)
+    int host_slabs = 8, host_slabs_forced = 0;        // upper bound on the number of slabs; RG_HOST_SLABS forces an exact count
+    int host_slab_min = 256;                          // RG_HOST_SLAB_MIN (smallest slab, pulses)
+    std::vector<cudaEvent_t> slab_events;             // reused by the pipelined host entry points
     cudaStream_t s_peer[2] = {nullptr, nullptr};      // side streams of rg_gather_to_peers (created on first use)
     cudaEvent_t ev_src = nullptr, ev_peer_join = nullptr, ev_gather[2] = {nullptr, nullptr};
     bool gather_pending[2] = {false, false};
