@@ -104,10 +104,16 @@ def optimize_fidelity_and_error_sources(fidelity_problem, fidelity_parameters, c
 
     opts = {"maxiter": int(prm.iterations)}
     ap = dict(prm.additional_parameters)
+    # Optim.Options names of the reference (src/FidelityCalculations.jl:219-231 passes additional_parameters straight through).
+    # g_tol -> gtol (both bound the infinity norm of the gradient).  f_abstol -> ftol: scipy's L-BFGS-B test is
+    # (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= ftol, and this cost lies in [0, 1 + O(coeff)], so the denominator is 1 and the test
+    # is the absolute one Optim applies.  Anything else has no scipy counterpart: rejected loudly rather than silently dropped.
     if "g_tol" in ap:
-        opts["gtol"] = ap["g_tol"]
+        opts["gtol"] = ap.pop("g_tol")
     if "f_abstol" in ap:
-        opts["ftol"] = ap["f_abstol"]
+        opts["ftol"] = ap.pop("f_abstol")
+    if ap:
+        raise ValueError(f"unsupported Optim option(s) {sorted(ap)}: only g_tol and f_abstol are mapped")
     try:
         return minimize(fg, x0, jac=True, method=prm.solver_algorithm, callback=cb, options=opts)
     except _Timeout:
