@@ -18,8 +18,10 @@ static int upload_reg(rg_problem* pr, const int32_t* kind, const double* c1, con
     std::vector<unsigned char> h((size_t)p * (sizeof(int) + 16));
     double* hc1 = reinterpret_cast<double*>(h.data()); double* hc2 = hc1 + p; int* hk = reinterpret_cast<int*>(hc2 + p);
     for (int i = 0; i < p; ++i) { hc1[i] = c1[i]; hc2[i] = c2[i]; hk[i] = kind[i]; }
+    if (h == pr->reg_host) return RG_OK;                   // same table as the last call (every evaluation of an optimiser run): no copy, no sync
     CU(ctx, cudaMemcpyAsync(pr->regbuf.p, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));           // h goes out of scope
+    pr->reg_host = h;
     return RG_OK;
 }
 static int launch_reg(rg_problem* pr, int B, const double* dX, double* dcost, double* dgrad) {

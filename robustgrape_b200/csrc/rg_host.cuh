@@ -87,6 +87,7 @@ struct rg_problem {
     int is_hstack = 0;            // closure problem: Hamiltonians arrive as host-evaluated stacks (rg_*_from_hstack)
     DevBuf dHs, dTs;
     DevBuf regbuf, lbfgs, dXopt;   // regularisation table, L-BFGS state, staged iterate (rg_api_optim.inl)
+    std::vector<unsigned char> reg_host;   // host copy of the table in regbuf
     int diag_alg = 0;             // projector and target are diagonal: elementwise fidelity algebra in the fused kernel
     int force_dense_alg = 0;      // RG_DENSE_ALG=1: dense fidelity algebra even then (A/B and tests)
     int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
