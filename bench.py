@@ -46,6 +46,22 @@ def make_problem(ntimes, nerr):
     return rg.FidelityRobustGRAPEProblem(up, PROJ, rt.cz_target())
 
 
+def make_model_problem(ntimes, d):
+    """The reference's other Rydberg models as descriptor problems: d = 7 full-blockaded (src/RydbergTools.jl:71-81), d = 9 full two-atom
+    model with finite blockade and detunings (:118-130); CZ target with a single-qubit phase, projector on the computational levels."""
+    import robustgrape_b200 as rg
+    from robustgrape_b200 import rydberg_tools as rt
+    if d == 7:
+        up = rg.UnitaryRobustGRAPEProblem(t0=T0, ntimes=ntimes, ndim=7, H0=rt.rydberg_h0("full_blockaded"), nb_additional_param=1, error_sources=[])
+        return rg.FidelityRobustGRAPEProblem(up, np.diag([1.0, 1, 1, 1, 0, 0, 0]), rt.cz_target("full_blockaded"))
+    from robustgrape_b200.descriptors import Factor, Term, TermTarget, S_ADD, OWNER_TARGET
+    tgt = TermTarget(9, [Term(1.0, (), ((0, 0, 1.0),), OWNER_TARGET),
+                         Term(1.0, (Factor.expi(S_ADD, 0, 1.0, 0.0),), ((1, 1, 1.0), (2, 2, 1.0)), OWNER_TARGET),
+                         Term(1.0, (Factor.expi(S_ADD, 0, 2.0, np.pi),), ((3, 3, 1.0),), OWNER_TARGET)])
+    up = rg.UnitaryRobustGRAPEProblem(t0=T0, ntimes=ntimes, ndim=9, H0=rt.rydberg_full_h0(1.0, 1.0, 0.0, 0.0, 8.0), nb_additional_param=1, error_sources=[])
+    return rg.FidelityRobustGRAPEProblem(up, np.diag([1.0, 1, 1, 1, 0, 0, 0, 0, 0]), tgt)
+
+
 def make_pulses(ntimes, batch, seed=43):
     """phi_k ~ 2 pi U(0,1) (test/runtests.jl:91), theta ~ 2 pi U(0,1); one pulse per row (C order)
     == one pulse per column of the (nx, B) column-major array the C ABI takes."""
@@ -455,8 +471,10 @@ def main():
         bs = args.batch // world
         return args.batch, bs, np.ascontiguousarray(make_pulses(N, args.batch)[rank * bs:(rank + 1) * bs])
 
-    def device_run(scaling, steps, warmup, sample_clocks):
-        """Times `steps` evaluations of this rank's shard, inputs resident in HBM; max over ranks."""
+    def device_run(scaling, steps, warmup, sample_clocks, what="all"):
+        """Times `steps` evaluations of this rank's shard, inputs resident in HBM; max over ranks.  what = "all": every rank's
+        [cost | grad] block is gathered on every rank each step (north_star); "costs": only the costs are (the gradients stay with
+        the rank whose optimiser consumes them)."""
         B, Bs, Xs = shard_inputs(scaling)
         dX = torch.from_numpy(Xs).to(dev)
         # inputs rotate over NROT distinct pulse sets so that, together with the double-buffered outputs, the bytes touched
@@ -464,6 +482,7 @@ def main():
         nrot = max(1, min(4, int(np.ceil(2 * 126e6 / max(1.0, Bs * nx * 8.0)))))
         dXs = [dX] + [torch.from_numpy(make_pulses(N, Bs, seed=1000 + 17 * r + rank)).to(dev) for r in range(1, nrot)]
         blk = Bs * (1 + nx)
+        gblk = blk if what == "all" else Bs                      # doubles gathered per rank and step
         # [cost (Bs) | grad (Bs, nx)] per rank; two buffers so that the gather of step i (side streams / NCCL's stream)
         # overlaps the kernels of step i+1: in multi-start optimisation a rank's next evaluation only needs its own shard.
         out_locals = [torch.empty(blk, dtype=torch.float64, device=dev) for _ in range(2)]
@@ -471,10 +490,10 @@ def main():
         out_alls = None
         if gather == "peer":
             from robustgrape_b200.sharding import PeerGather
-            pg = PeerGather(ctx, rank, world, blk, nbuf=2, mode=gather_mode)
+            pg = PeerGather(ctx, rank, world, gblk, nbuf=2, mode=gather_mode)
             out_alls = [pg.view(i, dev) for i in range(2)]
         elif gather == "nccl":
-            out_alls = [torch.empty(world * blk, dtype=torch.float64, device=dev) for _ in range(2)]
+            out_alls = [torch.empty(world * gblk, dtype=torch.float64, device=dev) for _ in range(2)]
         pending = [None, None]
         step_no = [0]
         flag = torch.zeros(1, dtype=torch.float32, device=dev) if pg is not None else None
@@ -495,7 +514,7 @@ def main():
             xin = dXs[(step_no[0] - 1) % len(dXs)]
             prob.cost_and_grad_batch_dev(Bs, nx, xin.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr())
             if gather == "nccl":
-                pending[i] = dist.all_gather_into_tensor(out_alls[i], ol, async_op=True)
+                pending[i] = dist.all_gather_into_tensor(out_alls[i], ol[:gblk], async_op=True)
             elif pg is not None:
                 pg.push(ol.data_ptr(), i)
 
@@ -539,8 +558,8 @@ def main():
         x_last = dXs[(step_no[0] - 1) % len(dXs)]
         if out_alls is not None:
             # the gathered buffer must hold every rank's block: check against one untimed NCCL all-gather
-            ref = torch.empty(world * blk, dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(ref, out_locals[last])
+            ref = torch.empty(world * gblk, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(ref, out_locals[last][:gblk])
             torch.cuda.synchronize()
             assert torch.equal(ref, out_alls[last]), f"rank {rank}: gathered [cost|grad] differs from NCCL all-gather"
             del ref
@@ -555,7 +574,8 @@ def main():
             cost_host = out_locals[last][:Bs].cpu().numpy()
         del dXs
         return {"B": B, "Bs": Bs, "Xs": Xs, "dX": dX, "ms": float(ms.item()), "launches": launches, "cost": cost_host,
-                "clocks": sampler.summary() if sampler else None, "out": out_locals[0]}
+                "clocks": sampler.summary() if sampler else None, "out": out_locals[0],
+                "gather_bytes_in_per_rank_per_step": (world - 1) * gblk * 8 if out_alls is not None or pg is not None or gather != "none" else 0}
 
     peak_dfma = peak_dmma = None
     if rank == 0:
@@ -575,6 +595,14 @@ def main():
             other = {"scaling": oscal, "batch": o["B"], "per_gpu_batch": o["Bs"], "ms_per_step": o["ms"] / args.steps,
                      "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3)}
             del o
+    costs_only = None
+    if world > 1 and not args.no_extra and gather != "none":
+        o = device_run(scaling, args.steps, args.warmup, False, what="costs")
+        costs_only = {"scaling": scaling, "ms_per_step": o["ms"] / args.steps, "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3),
+                      "gathered_bytes_in_per_rank_per_step": o["gather_bytes_in_per_rank_per_step"],
+                      "note": "same run with only the costs all-gathered (8 B per pulse); the gradients stay on the rank whose "
+                              "optimiser consumes them -- what multi-start optimisation needs; shows the kernels' own scaling"}
+        del o
 
     # ---- e2e: host buffers through the C ABI, H2D and D2H inside the timed region
     hX = torch.from_numpy(Xs).pin_memory()
@@ -627,6 +655,24 @@ def main():
             p1.close()
         except Exception as ex:      # noqa: BLE001
             extra = {"C4prime_e1_error": str(ex)}
+        # the reference's other two Rydberg models (src/RydbergTools.jl:71-81,118-130): 7-level full-blockaded (1+2+2+2 blocks, fused
+        # phase-only kernel) on the same batch, 9-level finite-blockade model (a 4-level block: general kernels) on 512 pulses
+        for key, d, bsz in (("model_d7", 7, Bs), ("model_d9", 9, min(Bs, 512))):
+            try:
+                pm = Problem(make_model_problem(N, d), ctx)
+                for _ in range(2):
+                    pm.cost_and_grad_batch_dev(bsz, nx, dX.data_ptr(), [], dcost.data_ptr(), dgrad.data_ptr())
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                k = max(2, args.steps // 2)
+                for _ in range(k):
+                    pm.cost_and_grad_batch_dev(bsz, nx, dX.data_ptr(), [], dcost.data_ptr(), dgrad.data_ptr())
+                f1.record()
+                torch.cuda.synchronize()
+                extra[key] = {"pulses": bsz, "evals_per_s": bsz * k / (f0.elapsed_time(f1) * 1e-3), "path": pm.path(nx)}
+                pm.close()
+            except Exception as ex:      # noqa: BLE001
+                extra[key + "_error"] = str(ex)
 
     # ---- the optimiser loop on the device: batched L-BFGS with X resident in HBM, sin^2 regularisation epilogue
     if not args.no_extra and rank == 0 and world == 1 and args.nerr == 0:
@@ -752,6 +798,20 @@ def main():
         if other:
             extra = dict(extra or {})
             extra[other["scaling"] + "_scaling"] = other
+        if world > 1 and gather != "none":
+            # the collective's own roofline: bytes every rank must receive per step over NVLink (ingress is the bound of an all-gather,
+            # with or without switch multicast) against the 900 GB/s per direction of NVLink 5
+            gb = run["gather_bytes_in_per_rank_per_step"]
+            step_s = ms_total / args.steps * 1e-3
+            line["gather"] = {"what": "[cost | grad] of every rank on every rank (north_star)", "how": gather,
+                              "bytes_in_per_rank_per_step": gb, "nvlink_ingress_GBps": gb / step_s / 1e9, "nvlink_peak_GBps": 900.0,
+                              "frac": gb / step_s / 1e9 / 900.0,
+                              "floor_ms_per_step": gb / 900e9 * 1e3,
+                              "note": "the step cannot be shorter than floor_ms_per_step while the full gradients are all-gathered; "
+                                      "extra.costs_only_gather shows the same run with 8 B per pulse gathered"}
+        if costs_only:
+            extra = dict(extra or {})
+            extra["costs_only_gather"] = costs_only
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:

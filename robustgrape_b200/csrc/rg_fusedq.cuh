@@ -207,43 +207,7 @@ __device__ __forceinline__ void qr_w(cplx (&w)[NB], const QS<NB>& g, const QS<NB
         w[n] = t;
     }
 }
-// sin and cos of one argument for the per-step phase: Cody-Waite reduction by pi/2 in three fused steps, the two minimax
-// polynomials of fdlibm's k_sin / k_cos on [-pi/4, pi/4], quadrant fix-up with selects.  Measured against long-double
-// sinl/cosl on 2e7 random arguments per range (|x| < 7, 100, 1e5): max error 1.58 ulp.  The library sincos() costs ~250 SASS
-// instructions per call here (coefficient tables through LDC, constants through UMOV pairs under the register cap), and after
-// the closed-form step constants the two calls per step were half of the kernel; this one is ~35.  |x| > 1e5 takes sincos().
-__constant__ double c_sc[16] = {
-    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,                      // 2/pi, pi/2 split in three
-    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
-    8.33333333332248946124e-03, -1.66666666666666324348e-01,                                                       // S6 .. S1
-    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
-    -1.38888888888741095749e-03, 4.16666666666666019037e-02};                                                      // C6 .. C1
-static __device__ __noinline__ double2 rg_sincos_slow(double x) { double2 r; sincos(x, &r.y, &r.x); return r; }
-// (coefficients come from the constant bank as DFMA operands: as literals each one costs a UMOV pair per use)
-__device__ __forceinline__ void rg_sincos_core(double x, double& s, double& c) {      // branch-free; valid for |x| <= 1e5
-    const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: the fma rounds x * 2/pi to the nearest integer
-    const double t = fma(x, c_sc[0], MAGIC);
-    const int q = __double2loint(t);
-    const double j = t - MAGIC;
-    double r = fma(-j, c_sc[1], x);
-    r = fma(-j, c_sc[2], r);
-    r = fma(-j, c_sc[3], r);
-    const double z = r * r;
-    double ps = fma(z, c_sc[4], c_sc[5]);
-    ps = fma(z, ps, c_sc[6]); ps = fma(z, ps, c_sc[7]); ps = fma(z, ps, c_sc[8]); ps = fma(z, ps, c_sc[9]);
-    const double sr = fma(r * z, ps, r);
-    double pc = fma(z, c_sc[10], c_sc[11]);
-    pc = fma(z, pc, c_sc[12]); pc = fma(z, pc, c_sc[13]); pc = fma(z, pc, c_sc[14]); pc = fma(z, pc, c_sc[15]);
-    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
-    // sign flips on the high words: s negative in quadrants 2, 3; c negative in quadrants 1, 2
-    s = __hiloint2double(__double2hiint(a) ^ ((q & 2) << 30), __double2loint(a));
-    c = __hiloint2double(__double2hiint(b) ^ (((q + 1) & 2) << 30), __double2loint(b));
-}
-__device__ __forceinline__ void rg_sincos(double x, double& s, double& c) {
-    if (fabs(x) > 1.0e5) { const double2 r = rg_sincos_slow(x); s = r.y; c = r.x; return; }
-    rg_sincos_core(x, s, c);
-}
+// (rg_sincos, rg_sincos_core: rg_common.cuh)
 // e^{ih} - 1 by its series, branch-free; valid for |h| < 1e-3 (truncation below 2e-22 relative)
 __device__ __forceinline__ cplx expm1i_small(double h) {
     const double h2 = h * h;

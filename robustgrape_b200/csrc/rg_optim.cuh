@@ -8,6 +8,7 @@
 //                  line-search round.  Role of Optim.optimize(...; method = LBFGS()) in src/FidelityCalculations.jl:199-217.
 #pragma once
 #include <cuda_runtime.h>
+#include "rg_common.cuh"
 
 // RG_REG_NONE / PLAIN / PHASE / SIN2 are declared in include/robustgrape_b200.h
 
@@ -58,7 +59,7 @@ k_regularize(int B, int nx, int p, int N, const int* __restrict__ kinds, const d
             if (i >= 0 && i < n) {
                 const double v = x[(size_t)i * p];
                 sx[j] = v;
-                if (kind == RG_REG_PHASE) sincos(v, &ss[j], &sc[j]);
+                if (kind == RG_REG_PHASE) rg_sincos(v, ss[j], sc[j]);
             }
         }
         __syncthreads();
@@ -95,12 +96,12 @@ k_regularize(int B, int nx, int p, int N, const int* __restrict__ kinds, const d
                 const int i = t0 - 1 + j;                                                                   // 1-based difference index
                 const bool own = (i >= t0 + 1 && i <= t1);                                                  // element i0 = i - 1 is in this tile
                 if (i >= 1 && i <= n - 1) {
-                    double sh, ch; sincos(0.5 * (xv(i) - xv(i - 1)), &sh, &ch);
+                    double sh, ch; rg_sincos(0.5 * (xv(i) - xv(i - 1)), sh, ch);
                     sc[j] = 2.0 * sh * ch;
                     if (own) r1 += sh * sh;
                 }
                 if (i >= 1 && i <= n - 2) {
-                    double sh, ch; sincos(0.5 * (xv(i + 1) - 2.0 * xv(i) + xv(i - 1)), &sh, &ch);
+                    double sh, ch; rg_sincos(0.5 * (xv(i + 1) - 2.0 * xv(i) + xv(i - 1)), sh, ch);
                     ss[j] = 2.0 * sh * ch;
                     if (own) r2 += sh * sh;
                 }
