@@ -172,7 +172,7 @@ def run_reference(args):
                                    "algorithm; Julia unavailable in this image)"},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world=1, scaling="weak", gather="peer"):
@@ -324,7 +324,7 @@ def run_dense(args):
                              "differences, so executed flops exceed the canonical (independent Pade exponentials) count; both are reported",
                      "kernel_ms": kernel_ms},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_response(args):
@@ -385,12 +385,35 @@ def run_response(args):
                                    "copies and the all-gather included"},
                 "e2e": {"value": 1e3 / ms, "unit": "sweeps/s", "h2d_bytes_per_step": int((N + 1) * 8 + nfreq * 8), "d2h_bytes_per_step": int(count * 2 * 8)},
                 "gpu_launches": int(ctx.launch_count)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries write banners to fd 1 (NCCL prints its version there under torchrun
+    whatever NCCL_DEBUG_FILE says).  Everything that is not the result line goes to stderr: fd 1 is pointed at fd 2 and the
+    result is written to a duplicate of the original fd 1."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -826,7 +849,7 @@ def main():
                                     "sample": f"first {sample} pulses of the workload, C++ port of the reference's literal "
                                               "algorithm (oracle/cpu_port.cpp); Julia is not installed in this image",
                                     "max_abs_cost_diff_vs_gpu": float(np.abs(c_cpu - cost_host[:sample]).max())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -51,6 +51,7 @@ extern "C" int rg_ctx_create(rg_ctx** out, int device) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char* s = getenv("RG_HOST_SLABS")) { c->host_slabs = std::max(1, atoi(s)); c->host_slabs_forced = 1; }
     if (const char* s = getenv("RG_HOST_SLAB_MIN")) c->host_slab_min = std::max(1, atoi(s));
+    if (const char* s = getenv("RG_GATHER_SPLIT")) c->gather_split = std::max(0, atoi(s));
     cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (const char* s = getenv("RG_WS_LIMIT_GB")) c->ws_limit = (size_t)atof(s) * ((size_t)1 << 30);
@@ -65,13 +66,14 @@ extern "C" void rg_ctx_destroy(rg_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < RG_PEER_STREAMS; i++) {
         if (c->s_peer[i]) cudaStreamDestroy(c->s_peer[i]);
-        if (c->ev_gather[i]) cudaEventDestroy(c->ev_gather[i]);
+        if (c->ev_peer_join[i]) cudaEventDestroy(c->ev_peer_join[i]);
     }
+    for (int i = 0; i < 2; i++)
+        if (c->ev_gather[i]) cudaEventDestroy(c->ev_gather[i]);
     for (auto& e : c->slab_events) cudaEventDestroy(e);
     if (c->ev_src) cudaEventDestroy(c->ev_src);
-    if (c->ev_peer_join) cudaEventDestroy(c->ev_peer_join);
     if (c->d_status) cudaFree(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     delete c;

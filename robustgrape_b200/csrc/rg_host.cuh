@@ -30,8 +30,10 @@ struct rg_ctx {
     int host_slabs = 8, host_slabs_forced = 0;        // upper bound on the number of slabs; RG_HOST_SLABS forces an exact count
     int host_slab_min = 256;                          // RG_HOST_SLAB_MIN (smallest slab, pulses)
     std::vector<cudaEvent_t> slab_events;             // reused by the pipelined host entry points
-    cudaStream_t s_peer[2] = {nullptr, nullptr};      // side streams of rg_gather_to_peers (created on first use)
-    cudaEvent_t ev_src = nullptr, ev_peer_join = nullptr, ev_gather[2] = {nullptr, nullptr};
+#define RG_PEER_STREAMS 8
+    cudaStream_t s_peer[RG_PEER_STREAMS] = {};        // side streams of rg_gather_to_peers (created on first use)
+    cudaEvent_t ev_src = nullptr, ev_peer_join[RG_PEER_STREAMS] = {}, ev_gather[2] = {nullptr, nullptr};
+    int gather_split = 0;                             // RG_GATHER_SPLIT: pieces per peer copy (0 = automatic)
     bool gather_pending[2] = {false, false};
     bool timing = false;
     struct Span { int kernel; cudaEvent_t e0, e1; };
