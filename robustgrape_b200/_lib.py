@@ -89,6 +89,7 @@ SIGNATURES = {
     "rg_gather_wait_on": (C.c_int, [_vp, C.c_int32, _vp]),
     "rg_measure_fp64_peak": (C.c_int, [_vp, C.c_double, _dp, _dp]),
     "rg_problem_path": (C.c_int, [_vp, C.c_char_p, C.c_int32]),
+    "rg_cost_and_grad_batch_dev_scatter": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.POINTER(C.c_void_p), C.c_uint64, C.c_int32]),
 }
 
 _lib = None
@@ -428,6 +429,20 @@ class Problem:
         self._keep_coeff = coeff
         self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch_dev(h, B, _vp(dX_ptr), _ptr(coeff) if self.nerr else None,
                                                              _vp(dcost_ptr), _vp(dgrad_ptr)))
+
+
+def _scatter_dev(self, B, nx, dX_ptr, error_source_coeff, dcost_ptr, dgrad_ptr, peer_ptrs, dst_offset_bytes, what):
+    """rg_cost_and_grad_batch_dev_scatter: evaluation whose [cost | grad] block also lands in the peers' gathered buffers
+    (peer_ptrs: device pointers of the other ranks' buffers; what = 0 costs only, 1 costs and gradients)."""
+    h, p = self.handle_for(nx)
+    cf = np.ascontiguousarray(error_source_coeff, dtype=np.float64)
+    self._keep_coeff = cf
+    arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(q)) for q in peer_ptrs])
+    self.ctx.check(self.ctx.lib.rg_cost_and_grad_batch_dev_scatter(h, int(B), _vp(dX_ptr), _ptr(cf) if self.nerr else None, _vp(dcost_ptr),
+                                                                  _vp(dgrad_ptr), len(peer_ptrs), arr, int(dst_offset_bytes), int(what)))
+
+
+Problem.cost_and_grad_batch_dev_scatter = _scatter_dev
 
 
 class HStackProblem:

@@ -473,6 +473,7 @@ static int run_dev(rg_problem* pr, int B, const double* dX, int mode, const doub
         d_coeff = pr->coeff.as<double>();
     }
     const bool want_grad = (mode == 1) || dFdx || dF2dx;
+    if (pl.slab < B) pr->peer_out.n = 0;          // the fused gather addresses whole batches only: the caller falls back to copies
     for (int b0 = 0; b0 < B; b0 += pl.slab) {
         const int bs = std::min(pl.slab, B - b0);
         int rc = dispatch_slab(pr, bs, pl, dX + (size_t)b0 * P.nx, mode, d_coeff, dF ? dF + b0 : nullptr,
@@ -495,6 +496,38 @@ extern "C" int rg_cost_and_grad_batch_dev(rg_problem* pr, int32_t B, const doubl
     if (!pr) return RG_ERR_INVALID;
     if (B < 0 || (B > 0 && (!dX || !dcost || !dgrad))) RG_FAIL(pr->ctx, RG_ERR_INVALID, "bad batch arguments");
     return run_dev(pr, B, dX, 1, err_coeff, dcost, dgrad, nullptr, nullptr);
+}
+
+// Evaluation + gather in one call (multi-GPU sharding of the batch).  Where the fused kernel writes the final cost and gradient
+// (block-2 problems without error sources: BASELINE.json configs[3]) the stores to the peers' buffers come from that kernel;
+// everywhere else the evaluation is followed by copy-engine pushes.  Either way the transfer is ordered on the context stream.
+extern "C" int rg_cost_and_grad_batch_dev_scatter(rg_problem* pr, int32_t B, const double* dX, const double* err_coeff, double* dcost,
+                                                  double* dgrad, int32_t npeers, void* const* peer_base, uint64_t dst_offset, int32_t what) {
+    if (!pr) return RG_ERR_INVALID;
+    rg_ctx* ctx = pr->ctx;
+    if (B < 0 || (B > 0 && (!dX || !dcost || !dgrad))) RG_FAIL(ctx, RG_ERR_INVALID, "bad batch arguments");
+    if (npeers < 0 || npeers > RG_MAX_PEER_OUT || (npeers > 0 && !peer_base) || (dst_offset & 7) || what < 0 || what > 1)
+        RG_FAIL(ctx, RG_ERR_INVALID, "bad scatter arguments (at most %d peers, offset in whole doubles, what = 0 | 1)", RG_MAX_PEER_OUT);
+    if (B == 0) return RG_OK;
+    const size_t nx = pr->dp.nx;
+    PeerOut po{};
+    po.n = npeers; po.grads = what;
+    for (int q = 0; q < npeers; ++q) {
+        if (!peer_base[q]) RG_FAIL(ctx, RG_ERR_INVALID, "null peer buffer");
+        po.cost[q] = reinterpret_cast<double*>(static_cast<char*>(peer_base[q]) + dst_offset);
+        po.grad[q] = po.cost[q] + B;
+    }
+    pr->peer_out = po;
+    pr->peer_out_done = 0;
+    const int rc = run_dev(pr, B, dX, 1, err_coeff, dcost, dgrad, nullptr, nullptr);
+    const bool fused = pr->peer_out_done != 0;
+    pr->peer_out = PeerOut{};
+    pr->peer_out_done = 0;
+    if (rc || fused || npeers == 0) return rc;
+    int r2 = rg_gather_to_peers(ctx, dcost, (uint64_t)B * 8, npeers, peer_base, dst_offset, 0, 0);
+    if (!r2 && what) r2 = rg_gather_to_peers(ctx, dgrad, (uint64_t)B * nx * 8, npeers, peer_base, dst_offset + (uint64_t)B * 8, 0, 0);
+    if (!r2) r2 = rg_gather_wait(ctx, 0);
+    return r2;
 }
 
 // Host-buffer entry points.  The batch is cut into slabs and pipelined over three streams:

@@ -64,6 +64,12 @@ struct DevProblem {
                                 // eps and at eps2
 };
 
+// Destinations of a fused evaluation + gather (rg_cost_and_grad_batch_dev_scatter): besides its own output the kernel stores the
+// cost of every pulse -- and, if `grads`, the gradient -- into the gathered buffers of up to RG_MAX_PEER_OUT peers (CUDA IPC
+// mappings: plain stores that travel over NVLink).  cost[q] / grad[q] point at this rank's slot in peer q's buffer.
+#define RG_MAX_PEER_OUT 15
+struct PeerOut { int n, grads; double* cost[RG_MAX_PEER_OUT]; double* grad[RG_MAX_PEER_OUT]; };
+
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ cplx cmk(double x, double y) { return make_double2(x, y); }
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmk(a.x + b.x, a.y + b.y); }

@@ -30,7 +30,7 @@ int prepare_fq(rg_problem* pr) {
     return RG_OK;
 }
 int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
-              double scale0, double scale0T, int do_grad) {
+              double scale0, double scale0T, int do_grad, const PeerOut* po_in) {
     rg_ctx* ctx = pr->ctx;
     constexpr int NB = b2_nblocks(D, UM);
     { int rc = prepare_fq(pr); if (rc) return rc; }
@@ -41,23 +41,26 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     const int role = err_role ? 1 : 0;
     // Per warps-per-pulse choice w: chunk length, shared memory (the staged controls need (N p + 32 w) doubles per pulse; a pulse
     // that does not fit is read from global memory instead) and resident CTAs/SM from the occupancy query -- all fixed per problem.
+    const PeerOut po = po_in ? *po_in : PeerOut{};
+    const int vsel = (po.n > 0 && po.grads) ? 1 : 0;          // variant 1: gradient staged through shared-memory rows (peer gradients)
     if (!pr->fq_ready) {
-        for (int wi = 0; wi < 3; ++wi) {
-            const int w = 1 << wi, Lw = (P.N + 32 * w - 1) / (32 * w);
-            bool xs = pr->stage_xs != 0;
-            size_t sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, xs);
-            if (sm > 200 * 1024) { xs = false; sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, xs); }
-            pr->fq_xs[wi] = xs ? 1 : 0; pr->fq_smem[wi] = sm;
-            for (int r = 0; r < 2; ++r) {
-                int occ = 1, rc = RG_OK;
+        for (int v = 0; v < 2; ++v)
+            for (int wi = 0; wi < 3; ++wi) {
+                const int w = 1 << wi, Lw = (P.N + 32 * w - 1) / (32 * w);
+                int flags = (pr->stage_xs ? 3 : 0) | (v ? 2 : 0);
+                size_t sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, flags != 0);
+                if (sm > 200 * 1024) { flags = v ? -1 : 0; sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, false); }
+                pr->fq_xs[v][wi] = flags; pr->fq_smem[v][wi] = sm;
+                for (int r = 0; r < 2; ++r) {
+                    int occ = 1, rc = RG_OK;
 #define RG_FQ_SET(ERRR, DAA, PCC) { rc = set_smem(ctx, k_fused_q<D, UM, ERRR, DAA, PCC>, sm); if (!rc) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused_q<D, UM, ERRR, DAA, PCC>, 128, sm); }
-                if (pc) { if (r) { if (da) RG_FQ_SET(true, true, true) else RG_FQ_SET(true, false, true) } else { if (da) RG_FQ_SET(false, true, true) else RG_FQ_SET(false, false, true) } }
-                else { if (r) { if (da) RG_FQ_SET(true, true, false) else RG_FQ_SET(true, false, false) } else { if (da) RG_FQ_SET(false, true, false) else RG_FQ_SET(false, false, false) } }
+                    if (pc) { if (r) { if (da) RG_FQ_SET(true, true, true) else RG_FQ_SET(true, false, true) } else { if (da) RG_FQ_SET(false, true, true) else RG_FQ_SET(false, false, true) } }
+                    else { if (r) { if (da) RG_FQ_SET(true, true, false) else RG_FQ_SET(true, false, false) } else { if (da) RG_FQ_SET(false, true, false) else RG_FQ_SET(false, false, false) } }
 #undef RG_FQ_SET
-                if (rc) return rc;
-                pr->fq_occ[r][wi] = std::max(1, occ);
+                    if (rc) return rc;
+                    pr->fq_occ[v][r][wi] = std::max(1, occ);
+                }
             }
-        }
         pr->fq_ready = 1;
     }
     // warps per pulse: cost = waves * (sweep steps per lane + fixed scan/algebra overhead of ~24 sweep steps)
@@ -65,7 +68,8 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     for (int wi = 0; wi < 3; ++wi) {
         const int w = 1 << wi;
         const int Lw = (P.N + 32 * w - 1) / (32 * w);
-        const double cap = (double)ctx->sm_count * pr->fq_occ[role][wi];
+        const double cap = (double)ctx->sm_count * pr->fq_occ[vsel][role][wi];
+        if (pr->fq_xs[vsel][wi] < 0) continue;                 // the staged rows of this choice do not fit
         const double ctas = std::ceil((double)B * w / 4.0) * (err_role ? P.e : 1);
         const double cost = std::ceil(ctas / cap) * (Lw + 24.0);
         if (cost < best) { best = cost; wpp = w; wsel = wi; }
@@ -73,11 +77,12 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     if (pr->wpp_override > 0) { wpp = pr->wpp_override >= 4 ? 4 : (pr->wpp_override >= 2 ? 2 : 1); wsel = wpp == 4 ? 2 : (wpp == 2 ? 1 : 0); }
     const int L = (P.N + 32 * wpp - 1) / (32 * wpp);
     const int ppc = 4 / wpp;
-    const size_t smem = pr->fq_smem[wsel];
-    const int use_xs = pr->fq_xs[wsel];
+    if (pr->fq_xs[vsel][wsel] < 0) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "fused gather of gradients: a pulse of %d steps does not fit the staged rows", P.N);
+    const size_t smem = pr->fq_smem[vsel][wsel];
+    const int use_xs = pr->fq_xs[vsel][wsel];
     dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? P.e : 1);
     KTimer kt(ctx, err_role ? RG_K_GRAD_ERR : RG_K_GRAD);
-#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, use_xs, ctx->d_status)
+#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, use_xs, po, ctx->d_status)
     if (pc) {
         if (err_role) { if (da) RG_FQ_GO(true, true, true); else RG_FQ_GO(true, false, true); }
         else { if (da) RG_FQ_GO(false, true, true); else RG_FQ_GO(false, false, true); }

@@ -543,7 +543,8 @@ struct FQDiag {
 template <int D, unsigned UMASK, bool ERR, bool DA, bool PC = false>
 __global__ void __launch_bounds__(128, PC ? (ERR ? RG_FQC_ERR_CTAS : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
 k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
-          int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int use_xs, int* __restrict__ status) {
+          int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int use_xs, const PeerOut po,
+          int* __restrict__ status) {
     constexpr int NB = b2_nblocks(D, UMASK);
     constexpr int DD = D * D;
     typedef QS<NB> Q;
@@ -571,7 +572,8 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
     double* xs = reinterpret_cast<double*>(slot + LY.xs);        // [32 wpp][S] staged controls, later the gradient
     const double* xp = X + (size_t)b * P.nx;
     const int Lp = L * P.p;
-    if (use_xs) {
+    const bool xs_in = (use_xs & 1) != 0, xs_out = (use_xs & 2) != 0;      // controls staged in / gradient staged out through the rows
+    if (xs_in) {
         // row r of the pulse = steps [rL, (r+1)L): warp wip takes rows wip, wip + wpp, ...; lanes run along the row (coalesced)
         for (int r = wip; r < 32 * wpp; r += wpp) {
             const int n = min(Lp, P.p * P.N - r * Lp);
@@ -580,7 +582,7 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
         __syncthreads();
     }
     // controls of step k of this lane's chunk: shared row t (or global memory when the pulse does not fit)
-    const double* xrow = use_xs ? xs + (size_t)t * LY.S - (size_t)min(P.N, t * L) * P.p : xp;
+    const double* xrow = xs_in ? xs + (size_t)t * LY.S - (size_t)min(P.N, t * L) * P.p : xp;
     double xadd[RG_MAX_ADD], xk[RG_MAX_MAIN];
     for (int j = 0; j < P.a; ++j) xadd[j] = xp[(size_t)P.p * P.N + j];
     const int k0 = min(P.N, t * L), k1 = min(P.N, k0 + L);
@@ -794,8 +796,9 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
 #pragma unroll
     for (int j = 0; j < RG_MAX_ADD; ++j) acc[j] = 0.0;
     double* outb = ERR ? out + ((size_t)b * ne + es) * P.nx : out + (size_t)b * P.nx;
-    double* grow = use_xs ? const_cast<double*>(xrow) : outb;          // gradient entry of step k replaces x_k in the staged row
-    const bool gput = use_xs || live;
+    // staged: the gradient entry of step k goes to (and, with xs_in, replaces x_k in) the lane's shared-memory row
+    double* grow = xs_out ? xs + (size_t)t * LY.S - (size_t)min(P.N, t * L) * P.p : outb;
+    const bool gput = xs_out || live;
     auto put_grad = [&](int k, int idx, double s) { if (gput) grow[(size_t)P.p * k + idx] = s; };
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
@@ -856,13 +859,21 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
             }
         }
     }
-    if (use_xs) {
+    if (xs_out) {
         __syncthreads();                                                   // all rows of the pulse hold gradient entries now
-        if (live)
-            for (int r = wip; r < 32 * wpp; r += wpp) {
-                const int n = min(Lp, P.p * P.N - r * Lp);
-                for (int c = lane; c < n; c += 32) outb[(size_t)r * Lp + c] = xs[r * LY.S + c];
+        // the pulse's 32 wpp lanes sweep its N p entries in order: full-line stores to the local output and, in a fused
+        // evaluation + gather, to this rank's slot in every peer's buffer (the stores travel over NVLink while other CTAs compute)
+        if (live) {
+            const int np_ = P.p * P.N;
+            const size_t go = ERR ? ((size_t)b * ne + es) * P.nx : (size_t)b * P.nx;
+            for (int g0 = t; g0 < np_; g0 += 32 * wpp) {
+                const int r = g0 / Lp;
+                const double v = xs[r * LY.S + (g0 - r * Lp)];
+                outb[g0] = v;
+                if (po.grads)
+                    for (int q = 0; q < po.n; ++q) po.grad[q][go + g0] = v;
             }
+        }
     }
     // ---- x_add entries: fixed-order reduction over the pulse's lanes, plus the target-derivative part from the algebra
     if (P.a > 0) {
@@ -877,7 +888,10 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
             double s = 0.0;
             for (int w2 = 0; w2 < wpp; ++w2) s += accS[w2 * RG_MAX_ADD + lane];
             if (P.add_var[lane] < 0) s = 0.0;
-            outb[(size_t)P.p * P.N + lane] = s + (ERR ? 1.0 : scale0T) * addT[lane];
+            const double v = s + (ERR ? 1.0 : scale0T) * addT[lane];
+            outb[(size_t)P.p * P.N + lane] = v;
+            if (po.grads)
+                for (int q = 0; q < po.n; ++q) po.grad[q][(ERR ? ((size_t)b * ne + es) * P.nx : (size_t)b * P.nx) + (size_t)P.p * P.N + lane] = v;
         }
     }
     if (Kmax == 99) {
@@ -885,5 +899,15 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
         // asynchronous *_dev entry points cannot consume an inaccurate value before they see the status (fail closed)
         atomicOr(status, 2);
         if (live) Fout[ERR ? (size_t)b * ne + es : (size_t)b] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    if (po.n > 0) {
+        // fused gather of the costs: after every lane of the pulse is past the poisoning above, one lane copies the pulse's
+        // cost to every peer
+        __syncthreads();
+        if (t == 0 && live) {
+            const size_t fi = ERR ? (size_t)b * ne + es : (size_t)b;
+            const double v = *reinterpret_cast<volatile double*>(Fout + fi);
+            for (int q = 0; q < po.n; ++q) po.cost[q][fi] = v;
+        }
     }
 }

@@ -94,8 +94,10 @@ struct rg_problem {
     int force_dense_alg = 0;      // RG_DENSE_ALG=1: dense fidelity algebra even then (A/B and tests)
     int wpp_override = 0;         // RG_WPP=1|2|4: warps per pulse of the fused quaternion kernel
     // fused quaternion kernel, per warps-per-pulse choice (1, 2, 4): resident CTAs/SM by role, shared memory, controls staged or not
-    int fq_ready = 0, fq_occ[2][3] = {{1, 1, 1}, {1, 1, 1}}, fq_xs[3] = {0, 0, 0};
-    size_t fq_smem[3] = {0, 0, 0};
+    int fq_ready = 0, fq_occ[2][2][3] = {}, fq_xs[2][3] = {};      // [variant: default | gradient staged out][role][wpp choice]
+    size_t fq_smem[2][3] = {};
+    PeerOut peer_out{};           // set by rg_cost_and_grad_batch_dev_scatter around one evaluation; peer_out_done: the kernel took it
+    int peer_out_done = 0;
     int stage_xs = 0;             // RG_XS=1: stage the controls (and the gradient) through shared-memory rows.  Measured on B200 and
                                   // rejected as the default: C4 0.240 ms staged vs 0.183 ms direct (the lane-strided global loads hit L1
                                   // three times out of four, and staging adds two CTA-wide barriers and a serial load/store phase)
@@ -136,7 +138,7 @@ void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas);
 // one-launch fused quaternion path (rg_fusedq.cuh): block-2 patterns without diagonal terms
 int rg_fq_pattern(const rg_problem* pr);
 int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
-                 double scale0, double scale0T, int do_grad);
+                 double scale0, double scale0T, int do_grad, const PeerOut* po = nullptr);
 int rg_fq_prepare(rg_problem* pr);
 static inline bool rg_use_b2(const rg_problem* pr) {
     return !pr->force_group && !pr->force_dense && !pr->force_group_sweeps && !pr->fused_agg && rg_b2_pattern(pr) != 0;
@@ -317,7 +319,10 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         const double DD1q = P.Dtr * (P.Dtr + 1.0);
         const double sgn = (mode == 1 && ne == 0) ? -1.0 : 1.0;
         const bool cost_fused = (mode == 1 && ne == 0);
-        int rc = rg_fq_launch(pr, P, B, dX, 0, cost_fused ? dF : iF, cost_fused ? 1 : 0, iFdx, sgn * P.inv_eps / DD1q, sgn, want_grad ? 1 : 0);
+        // fused evaluation + gather (rg_cost_and_grad_batch_dev_scatter): only where this launch writes the final cost and gradient
+        const PeerOut* po = (cost_fused && pr->peer_out.n > 0) ? &pr->peer_out : nullptr;
+        if (po) pr->peer_out_done = 1;
+        int rc = rg_fq_launch(pr, P, B, dX, 0, cost_fused ? dF : iF, cost_fused ? 1 : 0, iFdx, sgn * P.inv_eps / DD1q, sgn, want_grad ? 1 : 0, po);
         if (rc) return rc;
         if (ne > 0) { rc = rg_fq_launch(pr, P, B, dX, 1, iF2, 0, iF2dx, 0.0, 1.0, want_grad ? 1 : 0); if (rc) return rc; }
         if (mode == 1 && ne > 0) {

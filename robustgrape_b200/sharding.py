@@ -79,6 +79,13 @@ class PeerGather:
     def wait(self, slot):
         self.ctx.gather_wait(slot)
 
+    def scatter_targets(self, buf, include_self=True):
+        """(device pointers of buffer `buf` on the ranks to write to, byte offset of this rank's slot in each): the arguments of
+        Problem.cost_and_grad_batch_dev_scatter.  With include_self the rank's own gathered buffer is one of the destinations, so
+        after the call every buffer -- local and remote -- holds this rank's block at the same offset."""
+        targets = [q for r, q in enumerate(self.peers[buf]) if include_self or r != self.rank]
+        return targets, self.rank * self.block * 8
+
     def wait_on(self, slot, cuda_stream):
         """`cuda_stream` waits for this rank's pushes of `slot` (then a barrier there = cross-rank completion)."""
         self.ctx.gather_wait_on(slot, cuda_stream)

@@ -781,3 +781,39 @@ def test_reduced_vs_full_hamiltonian_on_gpu(gpu_ctx):
         assert np.abs(a[0] - b[0]).max() < 1e-12
         for k, u, v in zip(NAMES[1:], a[1:], b[1:]):
             assert relmax(u, v) < 1e-10, (errs, k, relmax(u, v))
+
+
+@pytest.mark.parametrize("what,nerr,B", [(1, 0, 37), (0, 0, 37), (1, 1, 9), (1, 0, 1)])
+def test_fused_evaluation_and_gather_single_process(gpu_ctx, what, nerr, B):
+    """rg_cost_and_grad_batch_dev_scatter: the [cost | grad] block of an evaluation must land, bit for bit, at the given offset of
+    every destination buffer -- from the evaluation kernel itself for e = 0 (fused stores, gradient staged through shared-memory
+    rows) and from copy-engine pushes otherwise -- and the local outputs must equal those of the plain call.  One process: the
+    'peers' are three more buffers on this device, viewed as slots of a world of 4 in which this rank is rank 2."""
+    import torch
+    from robustgrape_b200.unitary_calculations import device_problem
+    N = 101
+    fp = cz_problem(N, 7.613 * N / 1000 * 4, ("amp",)[:nerr])
+    dp = device_problem(fp, gpu_ctx)
+    nx, world, rank = N + 1, 4, 2
+    blk = B * (1 + nx)
+    dev = torch.device("cuda", gpu_ctx.device)
+    X = torch.from_numpy(np.ascontiguousarray((2 * np.pi * np.random.default_rng(B).random((nx, B))).T)).to(dev)
+    coeff = [1e-3] * nerr
+    ref = torch.zeros(blk, dtype=torch.float64, device=dev)
+    dp.cost_and_grad_batch_dev(B, nx, X.data_ptr(), coeff, ref[:B].data_ptr(), ref[B:].data_ptr())
+    bufs = [torch.full((world * blk,), -7.0, dtype=torch.float64, device=dev) for _ in range(3)]
+    loc = torch.zeros(blk, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    dp.cost_and_grad_batch_dev_scatter(B, nx, X.data_ptr(), coeff, loc[:B].data_ptr(), loc[B:].data_ptr(), [b.data_ptr() for b in bufs],
+                                       rank * blk * 8, what)
+    gpu_ctx.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(loc, ref)
+    for b in bufs:
+        got = b.view(world, blk)
+        assert torch.equal(got[rank, :B], ref[:B])
+        if what:
+            assert torch.equal(got[rank, B:], ref[B:])
+        else:
+            assert bool((got[rank, B:] == -7.0).all())
+        assert bool((got[[0, 1, 3]] == -7.0).all())
