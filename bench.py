@@ -124,7 +124,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)
 
     def __enter__(self):
         if self.nv:
@@ -569,16 +569,26 @@ def main():
             if pg is not None:
                 dist.all_reduce(flag)          # stream-ordered after the drained pushes of every rank: cross-rank completion
 
+        # The clock sampler (NVML, 20 Hz) starts before the warm-up and runs through the timed region: the GPU executes the same steps
+        # the whole time, so every sample is "under load".  It must not *start* at the timed region: its first query then always lands
+        # inside it, an NVML query holds up kernel launches for a few milliseconds, and at 20 steps of a 35 us shard that alone made
+        # the 8-GPU step 0.18 ms instead of 0.035 ms (measured).
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
         for _ in range(warmup):
             step()
+        t_spin = time.perf_counter()
+        while sample_clocks and time.perf_counter() - t_spin < 0.15:      # keep the GPU loaded until the barrier (untimed)
+            for _ in range(16):
+                step()
+            drain()
+            ctx.synchronize()
         drain()
         ctx.synchronize()
         barrier()
         l0 = ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.__enter__()
         e0.record()
         for _ in range(steps):
             step()
@@ -615,9 +625,12 @@ def main():
                 "clocks": sampler.summary() if sampler else None, "out": out_locals[0],
                 "gather_bytes_in_per_rank_per_step": (world - 1) * gblk * 8 if out_alls is not None or pg is not None or gather != "none" else 0}
 
-    peak_dfma = peak_dmma = None
-    if rank == 0:
-        peak_dfma, peak_dmma = ctx.measure_fp64_peak(0.3)
+    # Every rank runs the FP64 peak loops (0.3 s of full load): rank 0 reports them, and on all ranks they bring the SM clock up from
+    # idle before anything is timed -- with 20 steps of a 35 us shard the timed region is under a millisecond, and an idle GPU that is
+    # still ramping its clock made the max-over-ranks time of an 8-GPU run several times longer than the same run repeated.
+    peak_dfma, peak_dmma = ctx.measure_fp64_peak(0.3)
+    if rank != 0:
+        peak_dfma = peak_dmma = None
 
     scaling = args.scaling if world > 1 else "weak"
     run = device_run(scaling, args.steps, args.warmup, True)
