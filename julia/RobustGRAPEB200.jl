@@ -404,6 +404,35 @@ function cost_and_gradient_batch(fp::FidelityRobustGRAPEProblem, X::Matrix{Float
     return cost, grad
 end
 
+"Kernel family an evaluation of this problem takes (`rg_problem_path`): \"fused_q_pc\", \"fused_q\", \"block2\", \"steps_t\", \"group\", \"dense\", \"hstack\"."
+function kernel_path(fp::FidelityRobustGRAPEProblem, x::AbstractVector{Float64})
+    dp = device_problem(fp, x)
+    buf = zeros(UInt8, 32)
+    GC.@preserve buf check(dp.ctx, ccall((:rg_problem_path, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int32), dp.handle, buf, 32))
+    return unsafe_string(pointer(buf))
+end
+
+"Multi-start optimisation with the iterates resident on the device (`rg_lbfgs_batch`): one independent L-BFGS per column of X, the
+role of `Optim.optimize(...; method = LBFGS())` in src/FidelityCalculations.jl:199-217 for a whole batch.  `reg_kind[i]` selects the
+enumerated regularisation of control i (0 none, 1 regularization_cost, 2 regularization_cost_phase, 3 the tests' sin^2 form).
+Returns (X_final, cost, iterations per pulse)."
+function lbfgs_batch(fp::FidelityRobustGRAPEProblem, X0::Matrix{Float64}, error_source_coeff::Vector{Float64};
+                     reg_kind::Vector{Int32} = Int32[], reg_c1::Vector{Float64} = Float64[], reg_c2::Vector{Float64} = Float64[],
+                     history::Integer = 10, iterations::Integer = 100, g_tol::Float64 = 1e-8)
+    dp = device_problem(fp, view(X0, :, 1))
+    nx, B = size(X0)
+    X = copy(X0); cost = zeros(B); iters = zeros(Int32, B); info = zeros(Int32, 3)
+    GC.@preserve X cost iters info error_source_coeff reg_kind reg_c1 reg_c2 begin
+        check(dp.ctx, ccall((:rg_lbfgs_batch, LIB), Cint,
+                            (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64,
+                             Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                            dp.handle, B, X, isempty(error_source_coeff) ? C_NULL : pointer(error_source_coeff),
+                            isempty(reg_kind) ? C_NULL : pointer(reg_kind), isempty(reg_c1) ? C_NULL : pointer(reg_c1),
+                            isempty(reg_c2) ? C_NULL : pointer(reg_c2), history, iterations, g_tol, cost, iters, info))
+    end
+    return X, cost, iters
+end
+
 "Drop-in for RobustGRAPE.optimize_fidelity_and_error_sources (src/FidelityCalculations.jl:161-218): same closure
 structure, with the cost/gradient evaluation (:177-184) served by the GPU."
 function optimize_fidelity_and_error_sources(fp::FidelityRobustGRAPEProblem, prm::FidelityRobustGRAPEParameters)

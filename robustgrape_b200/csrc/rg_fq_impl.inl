@@ -47,7 +47,7 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
         for (int v = 0; v < 2; ++v)
             for (int wi = 0; wi < 3; ++wi) {
                 const int w = 1 << wi, Lw = (P.N + 32 * w - 1) / (32 * w);
-                int flags = (pr->stage_xs ? 3 : 0) | (v ? 2 : 0);
+                int flags = (pr->stage_xs == 1 ? 3 : (pr->stage_xs & 3)) | (v ? 2 : 0);      // RG_XS: 1 = stage in and out, 2 = out only, 3 = both
                 size_t sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, flags != 0);
                 if (sm > 200 * 1024) { flags = v ? -1 : 0; sm = fq_smem_bytes(D, NB, P.nterms, pr->tri.nent, pc, da, P.a, P.p, w, Lw, false); }
                 pr->fq_xs[v][wi] = flags; pr->fq_smem[v][wi] = sm;
