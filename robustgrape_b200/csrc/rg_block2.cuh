@@ -73,7 +73,7 @@ __device__ __forceinline__ cplx expm1i(double h) {
 template <int O>
 __device__ __forceinline__ void jexpi(const double* mu, cplx* E) {
     double s, c;
-    sincos(mu[0], &s, &c);
+    rg_sincos(mu[0], s, c);
     E[0] = cmk(c, s);
     if constexpr (O >= 1) {
         const cplx ea = expm1i(mu[1]);

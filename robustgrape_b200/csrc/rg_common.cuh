@@ -187,7 +187,7 @@ __device__ inline void factor_eval(const DevFactor& f, const EvalCtx& c, int psp
     if (f.kind == RG_F_VAR) { val = cmk(u, 0.0); del = cmk(hu, 0.0); return; }
     double s, co;
     if (c.ntrig > 0 && f.slot >= 0) { s = f.slot == 0 ? c.ts0 : c.ts1; co = f.slot == 0 ? c.tc0 : c.tc1; }
-    else sincos(u, &s, &co);
+    else rg_sincos(u, s, co);
     // e^{ihu} - 1 = -2 sin^2(hu/2) + i sin(hu)
     double er = 0.0, ei = 0.0;
     if (dep) {
