@@ -41,8 +41,8 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     const int role = err_role ? 1 : 0;
     // Per warps-per-pulse choice w: chunk length, shared memory (the staged controls need (N p + 32 w) doubles per pulse; a pulse
     // that does not fit is read from global memory instead) and resident CTAs/SM from the occupancy query -- all fixed per problem.
-    const PeerOut po = po_in ? *po_in : PeerOut{};
-    const int vsel = (po.n > 0 && po.grads) ? 1 : 0;          // variant 1: gradient staged through shared-memory rows (peer gradients)
+    PeerOut po = po_in ? *po_in : PeerOut{};
+    int vsel = (po.n > 0 && po.grads) ? 1 : 0;                // variant 1: gradient staged through shared-memory rows (peer gradients)
     if (!pr->fq_ready) {
         for (int v = 0; v < 2; ++v)
             for (int wi = 0; wi < 3; ++wi) {
@@ -63,6 +63,12 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
             }
         pr->fq_ready = 1;
     }
+    if (vsel == 1 && pr->fq_xs[1][0] < 0 && pr->fq_xs[1][1] < 0 && pr->fq_xs[1][2] < 0) {
+        // a pulse this long does not fit the staged rows in any configuration: evaluate without the fused gather (peer_out_done
+        // stays 0, so rg_cost_and_grad_batch_dev_scatter pushes the block with the copy engines afterwards)
+        po = PeerOut{}; vsel = 0;
+    }
+    if (po.n > 0) pr->peer_out_done = 1;
     // warps per pulse: cost = waves * (sweep steps per lane + fixed scan/algebra overhead of ~24 sweep steps)
     int wpp = 1, wsel = 0; double best = 1e300;
     for (int wi = 0; wi < 3; ++wi) {

@@ -320,8 +320,7 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         const double sgn = (mode == 1 && ne == 0) ? -1.0 : 1.0;
         const bool cost_fused = (mode == 1 && ne == 0);
         // fused evaluation + gather (rg_cost_and_grad_batch_dev_scatter): only where this launch writes the final cost and gradient
-        const PeerOut* po = (cost_fused && pr->peer_out.n > 0) ? &pr->peer_out : nullptr;
-        if (po) pr->peer_out_done = 1;
+        const PeerOut* po = (cost_fused && pr->peer_out.n > 0) ? &pr->peer_out : nullptr;      // the launcher sets peer_out_done if it takes it
         int rc = rg_fq_launch(pr, P, B, dX, 0, cost_fused ? dF : iF, cost_fused ? 1 : 0, iFdx, sgn * P.inv_eps / DD1q, sgn, want_grad ? 1 : 0, po);
         if (rc) return rc;
         if (ne > 0) { rc = rg_fq_launch(pr, P, B, dX, 1, iF2, 0, iF2dx, 0.0, 1.0, want_grad ? 1 : 0); if (rc) return rc; }

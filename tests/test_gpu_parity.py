@@ -783,16 +783,16 @@ def test_reduced_vs_full_hamiltonian_on_gpu(gpu_ctx):
             assert relmax(u, v) < 1e-10, (errs, k, relmax(u, v))
 
 
-@pytest.mark.parametrize("what,nerr,B", [(1, 0, 37), (0, 0, 37), (1, 1, 9), (1, 0, 1)])
-def test_fused_evaluation_and_gather_single_process(gpu_ctx, what, nerr, B):
+@pytest.mark.parametrize("what,nerr,B,N", [(1, 0, 37, 101), (0, 0, 37, 101), (1, 1, 9, 101), (1, 0, 1, 101), (1, 0, 3, 30000), (0, 0, 2, 30000)])
+def test_fused_evaluation_and_gather_single_process(gpu_ctx, what, nerr, B, N):
     """rg_cost_and_grad_batch_dev_scatter: the [cost | grad] block of an evaluation must land, bit for bit, at the given offset of
     every destination buffer -- from the evaluation kernel itself for e = 0 (fused stores, gradient staged through shared-memory
     rows) and from copy-engine pushes otherwise -- and the local outputs must equal those of the plain call.  One process: the
     'peers' are three more buffers on this device, viewed as slots of a world of 4 in which this rank is rank 2."""
     import torch
     from robustgrape_b200.unitary_calculations import device_problem
-    N = 101
-    fp = cz_problem(N, 7.613 * N / 1000 * 4, ("amp",)[:nerr])
+    # N = 30000: a pulse's gradient no longer fits the staged shared-memory rows -> evaluation without the fused stores + copy-engine pushes
+    fp = cz_problem(N, 7.613 * min(N, 2000) / 1000 * 4, ("amp",)[:nerr])
     dp = device_problem(fp, gpu_ctx)
     nx, world, rank = N + 1, 4, 2
     blk = B * (1 + nx)
