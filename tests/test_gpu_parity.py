@@ -817,3 +817,31 @@ def test_fused_evaluation_and_gather_single_process(gpu_ctx, what, nerr, B, N):
         else:
             assert bool((got[rank, B:] == -7.0).all())
         assert bool((got[[0, 1, 3]] == -7.0).all())
+
+
+def test_reference_gradient_validation_testsets_on_gpu(gpu_ctx):
+    """The two finite-difference testsets of the reference, statement for statement, on the CUDA path:
+    test/runtests.jl:48-111 (error-sensitivity gradient: N = 200, t0 = 2 pi 1.22, amplitude error, perturbation 1e-4, rtol 1e-3 /
+    atol 1e-5, the last test on the additional parameter) and :292-352 (fidelity gradient: N = 50, perturbation = the problem's
+    eps = 1e-8, rtol 1e-3 / atol 1e-3, the last of five tests on the additional parameter)."""
+    t0 = 2 * np.pi * 1.22
+    rng = np.random.default_rng(42)
+    # error sensitivity gradient
+    fp = cz_problem(200, t0, ("amp",))
+    for ntest in range(2):
+        idx = 200 if ntest == 1 else int(rng.integers(0, 200))
+        xs = 2 * np.pi * rng.random(201)
+        _, _, s0, s0dx = rg.calculate_fidelity_and_derivatives(fp, xs)
+        xs[idx] += 1e-4
+        _, _, s1, _ = rg.calculate_fidelity_and_derivatives(fp, xs)
+        assert np.isclose((s1[0] - s0[0]) / 1e-4, np.asarray(s0dx)[idx, 0], rtol=1e-3, atol=1e-5), (idx, (s1[0] - s0[0]) / 1e-4, np.asarray(s0dx)[idx, 0])
+    # fidelity gradient
+    fp = cz_problem(50, t0)
+    eps = fp.unitary_problem.eps
+    for ntest in range(5):
+        idx = 50 if ntest == 4 else int(rng.integers(0, 50))
+        xs = 2 * np.pi * rng.random(51)
+        F0, g0, _, _ = rg.calculate_fidelity_and_derivatives(fp, xs)
+        xs[idx] += eps
+        F1 = rg.calculate_fidelity_and_derivatives(fp, xs)[0]
+        assert np.isclose((F1 - F0) / eps, np.asarray(g0)[idx], rtol=1e-3, atol=1e-3), (idx, (F1 - F0) / eps, np.asarray(g0)[idx])
