@@ -538,10 +538,12 @@ struct SlabPipe {
     // events live in the context and are reused by every call (creating 2 x nslab of them per call cost tens of microseconds
     // of a ~1.5 ms evaluation)
     SlabPipe(rg_ctx* c, int B) : ctx(c), ev(c->slab_events) {
-        // fill/drain of the H2D | kernels | D2H pipeline costs 1/nslab of the copy time, every slab a fixed enqueue cost: measured on
-        // B200 (C4, PCIe ceiling 1.49 ms for both directions): 8192 pulses 1.84 ms with 4 slabs, 1.86 with 8, 2.03 with 16; 1024 pulses
-        // 0.36 ms with 1 slab, 0.30 with 4 x 256.  So: about 2048 pulses per slab, at least 4 slabs, none below host_slab_min.
-        const int target = c->host_slabs_forced ? c->host_slabs : std::max(4, std::min(c->host_slabs, B / 2048));
+        // fill/drain of the H2D | kernels | D2H pipeline costs 1/nslab of the copy time, every slab a fixed cost of ~25 us: measured on
+        // B200 (C4, PCIe ceiling 1.34 ms for both directions, costs copied once per call): 8192 pulses 1.75 ms with 8 slabs, 1.77 with 4,
+        // 1.86 with 16; 1024 pulses 0.36 ms with 1 slab, 0.31 with 4 x 256.  So: about 1024 pulses per slab, 4 to 8 slabs, none below
+        // host_slab_min.  (Rejected: a zero-copy variant in which the fused kernel reads X and writes the gradient directly in pinned
+        // host memory through staged full-line accesses -- 2.57 ms: SM-issued PCIe reads do not reach the copy engines' rate.)
+        const int target = c->host_slabs_forced ? c->host_slabs : std::max(4, std::min(c->host_slabs, B / 1024));
         nslab = std::max(1, std::min(target, B / std::max(1, c->host_slab_min)));
         per = (B + nslab - 1) / nslab;
         nslab = (B + per - 1) / per;
@@ -622,9 +624,10 @@ extern "C" int rg_cost_and_grad_batch(rg_problem* pr, int32_t B, const double* X
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(ctx, cudaEventRecord(sp.ev[2 * s + 1], ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->s_out, sp.ev[2 * s + 1], 0));
-        CU(ctx, cudaMemcpyAsync(cost + b0, o + b0, bs * 8, cudaMemcpyDeviceToHost, ctx->s_out));
         CU(ctx, cudaMemcpyAsync(grad + b0 * nx, o + B + b0 * nx, bs * nx * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    // the costs (8 B per pulse) leave in one copy behind the last slab instead of one small copy per slab
+    CU(ctx, cudaMemcpyAsync(cost, o, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     CU(ctx, cudaStreamSynchronize(ctx->s_out));
     int rcs = rg_ctx_synchronize(ctx);
     if (rcs == RG_ERR_NORM && pr->tri_ok && !pr->force_group) {
