@@ -247,7 +247,7 @@ def run_dense(args):
     """--workload C5 | d16: one pulse of the synthetic dense problem (d = 64 or 16, N = 1e4, p = 8, e = 4) on the DMMA path."""
     import torch
     from robustgrape_b200._lib import Context, Problem
-    d = 64 if args.workload == "C5" else 16
+    d = {"C5": 64, "d16": 16, "d32": 32, "d48": 48}[args.workload]
     N, p, e = args.dense_ntimes, 8, 4
     fp, x, nrm = make_dense_problem(d, N, p, e, args.dense_norm)
     ctx = Context(0)
@@ -428,8 +428,8 @@ def main():
     ap.add_argument("--cpu-pulses-per-thread", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16", "C3"],
-                    help="C4 (default): multi-start CZ batch, the headline; C5 / d16: dense synthetic problem on the DMMA path (1 GPU)")
+    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16", "d32", "d48", "C3"],
+                    help="C4 (default): multi-start CZ batch, the headline; C5 / d16 / d32 / d48: dense synthetic problem (d = 64 / 16 / 32 / 48) on the DMMA path (1 GPU)")
     ap.add_argument("--dense-ntimes", type=int, default=10000)
     ap.add_argument("--dense-norm", type=float, default=2.4, help="max_k ||dt H(k)||_1 of the dense workload (SURVEY 8d: 2.1 ... 5.4)")
     ap.add_argument("--dense-batch", type=int, default=1)

@@ -317,8 +317,14 @@ __device__ __noinline__ void jet_lincomb_T(double* Z, double c0, double c1, doub
 #ifndef RG_BIG16_CTAS
 #define RG_BIG16_CTAS 8       // d <= 16: 64-thread CTAs; measured on B200 (d16 workload): uncapped (164 registers, 6 CTAs/SM) 30.2 ms,
 #endif                        // 8 CTAs/SM (128 registers, no spills) 28.6 ms, 12 CTAs/SM (80 registers, spills) 37.8 ms
+#ifndef RG_BIG32_CTAS
+#define RG_BIG32_CTAS 4       // d <= 32: 128-thread CTAs; measured (d32 workload): uncapped (190 registers, 2 CTAs/SM) 200 ms, 3 CTAs/SM 164 ms,
+#endif                        // 4 CTAs/SM (128 registers, no spills) 161 ms = 0.57 of DMMA peak
+#ifndef RG_BIG48_CTAS
+#define RG_BIG48_CTAS 2
+#endif
 template <int DP>
-__global__ void __launch_bounds__(BigGemm<DP>::NT, DP <= 16 ? RG_BIG16_CTAS : 2)
+__global__ void __launch_bounds__(BigGemm<DP>::NT, DP <= 16 ? RG_BIG16_CTAS : (DP <= 32 ? RG_BIG32_CTAS : (DP <= 48 ? RG_BIG48_CTAS : 2)))
 k_big_steps(const DevProblem P, const BigData Bd, const double* __restrict__ X, int B, double* __restrict__ ws, int* __restrict__ status) {
     constexpr int NT = BigGemm<DP>::NT;
     extern __shared__ double smd[];
