@@ -316,7 +316,7 @@ __device__ __noinline__ void jet_lincomb_T(double* Z, double c0, double c1, doub
 // ---- k_big_steps: one persistent CTA per (pulse, step) task ---------------------------------------------------------------
 #ifndef RG_BIG16_CTAS
 #define RG_BIG16_CTAS 8       // d <= 16: 64-thread CTAs; measured on B200 (d16 workload): uncapped (164 registers, 6 CTAs/SM) 30.2 ms,
-#endif                        // 8 CTAs/SM (128 registers, no spills) 28.6 ms, 12 CTAs/SM (80 registers, spills) 37.8 ms
+#endif                        // 8 CTAs/SM (128 registers, no spills) 28.6 ms, 9-10 CTAs/SM 35.4 ms, 12 CTAs/SM (80 registers, spills) 37.8 ms
 #ifndef RG_BIG32_CTAS
 #define RG_BIG32_CTAS 4       // d <= 32: 128-thread CTAs; measured (d32 workload): uncapped (190 registers, 2 CTAs/SM) 200 ms, 3 CTAs/SM 164 ms,
 #endif                        // 4 CTAs/SM (128 registers, no spills) 161 ms = 0.57 of DMMA peak
