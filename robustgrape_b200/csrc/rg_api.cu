@@ -331,6 +331,7 @@ extern "C" int rg_problem_create(rg_ctx* ctx, const rg_problem_desc* desc, rg_pr
     if (const char* s = getenv("RG_B2")) pr->force_b2 = atoi(s);
     if (const char* s = getenv("RG_WPP")) pr->wpp_override = atoi(s);
     if (const char* s = getenv("RG_XS")) pr->stage_xs = atoi(s);
+    if (const char* s = getenv("RG_NO_ACCUM")) pr->no_accum = atoi(s);
     if (const char* s = getenv("RG_DENSE_ALG")) pr->force_dense_alg = atoi(s);
     {
         bool diag = desc->projector != nullptr && pr->has_target;

@@ -49,10 +49,10 @@ int rg_fq_pattern(const rg_problem* pr) {
     return (p == 1 || p == 3) ? p : 0;
 }
 int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
-                 double scale0, double scale0T, int do_grad, const PeerOut* po) {
+                 double scale0, double scale0T, int do_grad, const PeerOut* po, const FQAccum* ac) {
     switch (rg_fq_pattern(pr)) {
-    case 1: return rg_fq_ops_p1.launch(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad, po);
-    case 3: return rg_fq_ops_p3.launch(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad, po);
+    case 1: return rg_fq_ops_p1.launch(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad, po, ac);
+    case 3: return rg_fq_ops_p3.launch(pr, P, B, dX, err_role, Fout, fmode, out, scale0, scale0T, do_grad, po, ac);
     default: pr->ctx->err = "internal: fused quaternion path without an eligible pattern"; return RG_ERR_INVALID;
     }
 }

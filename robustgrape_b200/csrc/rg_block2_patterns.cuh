@@ -14,7 +14,7 @@ struct B2Ops {
     void (*occupancy)(const rg_problem*, int*, int*);
 };
 struct FQOps {
-    int (*launch)(rg_problem*, const DevProblem&, int, const double*, int, double*, int, double*, double, double, int, const PeerOut*);
+    int (*launch)(rg_problem*, const DevProblem&, int, const double*, int, double*, int, double*, double, double, int, const PeerOut*, const FQAccum*);
     int (*prepare)(rg_problem*);
 };
 extern const B2Ops rg_b2_ops_p1, rg_b2_ops_p2, rg_b2_ops_p3, rg_b2_ops_p4;

@@ -70,6 +70,11 @@ struct DevProblem {
 #define RG_MAX_PEER_OUT 15
 struct PeerOut { int n, grads; double* cost[RG_MAX_PEER_OUT]; double* grad[RG_MAX_PEER_OUT]; };
 
+// Cost/gradient assembly inside the error-role launch of the fused kernel (calculate_common!, src/FidelityCalculations.jl:178-184):
+// with `on`, the launch of error source es0 adds coeff[es0] F2^2 to cost[b] and 2 coeff[es0] F2 dF2/dx to the gradient the
+// fidelity-role launch left in `out` (= -dF/dx), instead of writing dF2/dx for a separate epilogue kernel to combine.
+struct FQAccum { int on, es0; const double* coeff; double* cost; };
+
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ cplx cmk(double x, double y) { return make_double2(x, y); }
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cmk(a.x + b.x, a.y + b.y); }

@@ -30,7 +30,7 @@ int prepare_fq(rg_problem* pr) {
     return RG_OK;
 }
 int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
-              double scale0, double scale0T, int do_grad, const PeerOut* po_in) {
+              double scale0, double scale0T, int do_grad, const PeerOut* po_in, const FQAccum* ac_in) {
     rg_ctx* ctx = pr->ctx;
     constexpr int NB = b2_nblocks(D, UM);
     { int rc = prepare_fq(pr); if (rc) return rc; }
@@ -76,7 +76,7 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
         const int Lw = (P.N + 32 * w - 1) / (32 * w);
         const double cap = (double)ctx->sm_count * pr->fq_occ[vsel][role][wi];
         if (pr->fq_xs[vsel][wi] < 0) continue;                 // the staged rows of this choice do not fit
-        const double ctas = std::ceil((double)B * w / 4.0) * (err_role ? P.e : 1);
+        const double ctas = std::ceil((double)B * w / 4.0) * (err_role ? ((ac_in && ac_in->on) ? 1 : P.e) : 1);
         const double cost = std::ceil(ctas / cap) * (Lw + 24.0);
         if (cost < best) { best = cost; wpp = w; wsel = wi; }
     }
@@ -86,9 +86,12 @@ int launch_fq(rg_problem* pr, const DevProblem& P, int B, const double* dX, int 
     if (pr->fq_xs[vsel][wsel] < 0) RG_FAIL(ctx, RG_ERR_UNSUPPORTED, "fused gather of gradients: a pulse of %d steps does not fit the staged rows", P.N);
     const size_t smem = pr->fq_smem[vsel][wsel];
     const int use_xs = pr->fq_xs[vsel][wsel];
-    dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? P.e : 1);
+    FQAccum ac = ac_in ? *ac_in : FQAccum{0, 0, nullptr, nullptr};
+    if (use_xs != 0) ac.on = 0;                                   // (the host only asks for it on the unstaged path)
+    if (ac_in && ac_in->on && !ac.on) RG_FAIL(ctx, RG_ERR_INVALID, "internal: in-kernel cost assembly on the staged path");
+    dim3 grid((unsigned)((B + ppc - 1) / ppc), err_role ? (ac.on ? 1 : P.e) : 1);
     KTimer kt(ctx, err_role ? RG_K_GRAD_ERR : RG_K_GRAD);
-#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, use_xs, po, ctx->d_status)
+#define RG_FQ_GO(ERRR, DAA, PCC) k_fused_q<D, UM, ERRR, DAA, PCC><<<grid, 128, smem, ctx->stream>>>(Pl, pr->tri, dX, B, wpp, L, Fout, fmode, out, scale0, scale0T, do_grad, use_xs, po, ac, ctx->d_status)
     if (pc) {
         if (err_role) { if (da) RG_FQ_GO(true, true, true); else RG_FQ_GO(true, false, true); }
         else { if (da) RG_FQ_GO(false, true, true); else RG_FQ_GO(false, false, true); }

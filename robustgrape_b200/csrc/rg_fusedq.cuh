@@ -544,7 +544,7 @@ template <int D, unsigned UMASK, bool ERR, bool DA, bool PC = false>
 __global__ void __launch_bounds__(128, PC ? (ERR ? RG_FQC_ERR_CTAS : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
 k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
           int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int use_xs, const PeerOut po,
-          int* __restrict__ status) {
+          const FQAccum ac, int* __restrict__ status) {
     constexpr int NB = b2_nblocks(D, UMASK);
     constexpr int DD = D * D;
     typedef QS<NB> Q;
@@ -559,7 +559,8 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
     const bool live = b < B;
     if (!live) b = B - 1;
     const int t = wip * 32 + lane;                               // lane within the pulse = chunk index
-    const int es = ERR ? (int)blockIdx.y : 0;
+    const int es = ERR ? ac.es0 + (int)blockIdx.y : 0;
+    const bool accum = ERR && ac.on;                             // add this source's terms to the final cost / gradient (FQAccum)
     const int ne = P.e, nv = P.nvar;
     const FQSlot LY = fq_slot(D, NB, DA, P.a, P.p, wpp, L, use_xs != 0);
     cplx* slot = smem + plan_cplx + (size_t)pslot * LY.slot;
@@ -733,6 +734,10 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
                 if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
                 else Fout[(size_t)b * ne + es] = Fval;
             }
+            if (accum) {
+                addT[RG_MAX_ADD] = Fval;                // F2 of this pulse for every lane's gradient scale
+                if (live) ac.cost[b] = fma(ac.coeff[es] * Fval, Fval, ac.cost[b]);
+            }
             for (int j = 0; j < P.a; ++j) {             // target-derivative part of the x_add[j] entry (:35-40,72-74,102-109)
                 double wj[D];
                 cplx t3 = cmk(0.0, 0.0);
@@ -755,6 +760,10 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
             if (live && lane == 0) {
                 if constexpr (!ERR) Fout[b] = fmode ? 1.0 - Fval : Fval;
                 else Fout[(size_t)b * ne + es] = Fval;
+            }
+            if (accum && lane == 0) {
+                addT[RG_MAX_ADD] = Fval;
+                if (live) ac.cost[b] = fma(ac.coeff[es] * Fval, Fval, ac.cost[b]);
             }
         }
         __syncthreads();
@@ -795,11 +804,17 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
     double acc[RG_MAX_ADD];
 #pragma unroll
     for (int j = 0; j < RG_MAX_ADD; ++j) acc[j] = 0.0;
-    double* outb = ERR ? out + ((size_t)b * ne + es) * P.nx : out + (size_t)b * P.nx;
+    double* outb = (ERR && !accum) ? out + ((size_t)b * ne + es) * P.nx : out + (size_t)b * P.nx;
     // staged: the gradient entry of step k goes to (and, with xs_in, replaces x_k in) the lane's shared-memory row
     double* grow = xs_out ? xs + (size_t)t * LY.S - (size_t)min(P.N, t * L) * P.p : outb;
     const bool gput = xs_out || live;
-    auto put_grad = [&](int k, int idx, double s) { if (gput) grow[(size_t)P.p * k + idx] = s; };
+    const double gscale = accum ? 2.0 * ac.coeff[es] * addT[RG_MAX_ADD] : 0.0;      // 2 c_e F2_e (every lane, after the barrier above)
+    auto put_grad = [&](int k, int idx, double s) {
+        if (gput) {
+            double* gp = grow + (size_t)P.p * k + idx;
+            *gp = accum ? fma(gscale, s, *gp) : s;             // each entry is owned by one lane; the launches of different sources are serial
+        }
+    };
     const double DD1 = P.Dtr * (P.Dtr + 1.0);
     const double f1 = 2.0 / DD1 * P.inv_eps * P.inv_eps, f2 = 2.0 / DD1 * P.inv_eps2sq;
     if constexpr (PC) {
@@ -888,7 +903,8 @@ k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const doubl
             double s = 0.0;
             for (int w2 = 0; w2 < wpp; ++w2) s += accS[w2 * RG_MAX_ADD + lane];
             if (P.add_var[lane] < 0) s = 0.0;
-            const double v = s + (ERR ? 1.0 : scale0T) * addT[lane];
+            double v = s + (ERR ? 1.0 : scale0T) * addT[lane];
+            if (accum) v = fma(gscale, v, outb[(size_t)P.p * P.N + lane]);
             outb[(size_t)P.p * P.N + lane] = v;
             if (po.grads)
                 for (int q = 0; q < po.n; ++q) po.grad[q][(ERR ? ((size_t)b * ne + es) * P.nx : (size_t)b * P.nx) + (size_t)P.p * P.N + lane] = v;

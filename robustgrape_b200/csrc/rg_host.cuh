@@ -98,6 +98,7 @@ struct rg_problem {
     size_t fq_smem[2][3] = {};
     PeerOut peer_out{};           // set by rg_cost_and_grad_batch_dev_scatter around one evaluation; peer_out_done: the kernel took it
     int peer_out_done = 0;
+    int no_accum = 0;             // RG_NO_ACCUM=1: separate dF2/dx buffer and k_cost_grad epilogue instead of in-kernel cost/gradient assembly
     int stage_xs = 0;             // RG_XS=1: stage the controls (and the gradient) through shared-memory rows.  Measured on B200 and
                                   // rejected as the default: C4 0.240 ms staged vs 0.183 ms direct (the lane-strided global loads hit L1
                                   // three times out of four, and staging adds two CTA-wide barriers and a serial load/store phase)
@@ -138,7 +139,7 @@ void rg_b2_occupancy(const rg_problem* pr, int* agg_ctas, int* grad_ctas);
 // one-launch fused quaternion path (rg_fusedq.cuh): block-2 patterns without diagonal terms
 int rg_fq_pattern(const rg_problem* pr);
 int rg_fq_launch(rg_problem* pr, const DevProblem& P, int B, const double* dX, int err_role, double* Fout, int fmode, double* out,
-                 double scale0, double scale0T, int do_grad, const PeerOut* po = nullptr);
+                 double scale0, double scale0T, int do_grad, const PeerOut* po = nullptr, const FQAccum* ac = nullptr);
 int rg_fq_prepare(rg_problem* pr);
 static inline bool rg_use_b2(const rg_problem* pr) {
     return !pr->force_group && !pr->force_dense && !pr->force_group_sweeps && !pr->fused_agg && rg_b2_pattern(pr) != 0;
@@ -321,6 +322,21 @@ static int run_slab(rg_problem* pr, int B, const Plan& pl, const double* dX, int
         const bool cost_fused = (mode == 1 && ne == 0);
         // fused evaluation + gather (rg_cost_and_grad_batch_dev_scatter): only where this launch writes the final cost and gradient
         const PeerOut* po = (cost_fused && pr->peer_out.n > 0) ? &pr->peer_out : nullptr;      // the launcher sets peer_out_done if it takes it
+        if (mode == 1 && ne > 0 && want_grad && !pr->stage_xs && !pr->no_accum && rg_fq_pattern(pr) == 1) {
+            // cost and gradient assembled by the launches themselves: the fidelity role leaves 1 - F and -dF/dx in the outputs, every
+            // error source's launch (one after the other: they update the same entries) adds c_e F2^2 and 2 c_e F2 dF2/dx.  No dF2/dx
+            // buffer, no epilogue kernel.  Measured on B200 (C4', 8192 x 1000, e = 1): 0.449 ms vs 0.487 ms with k_cost_grad; for the
+            // 7-level model the read-modify-write in the three-block error sweep costs more than the epilogue saves (0.727 vs 0.700 ms),
+            // so only the two-block pattern takes this path.
+            int rc = rg_fq_launch(pr, P, B, dX, 0, dF, 1, iFdx, -P.inv_eps / DD1q, -1.0, 1);
+            for (int e = 0; e < ne && !rc; ++e) {
+                const FQAccum ac{1, e, d_coeff, dF};
+                rc = rg_fq_launch(pr, P, B, dX, 1, iF2, 0, iFdx, 0.0, 1.0, 1, nullptr, &ac);
+            }
+            if (rc) return rc;
+            CU(ctx, cudaGetLastError());
+            return RG_OK;
+        }
         int rc = rg_fq_launch(pr, P, B, dX, 0, cost_fused ? dF : iF, cost_fused ? 1 : 0, iFdx, sgn * P.inv_eps / DD1q, sgn, want_grad ? 1 : 0, po);
         if (rc) return rc;
         if (ne > 0) { rc = rg_fq_launch(pr, P, B, dX, 1, iF2, 0, iF2dx, 0.0, 1.0, want_grad ? 1 : 0); if (rc) return rc; }
