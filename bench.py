@@ -330,6 +330,57 @@ def run_dense(args):
     emit(line)
 
 
+def run_single_pulse(args):
+    """--workload C1 | C2 (BASELINE.json configs[0], configs[1]): one pulse through the reference-signature call
+    calculate_fidelity_and_derivatives (host buffers in and out, blocking): the latency-bound single-pulse points.
+    C1 = examples/time_optimal_cz.jl (N = 500, t0 = 7.613, e = 0), C2 = examples/ar_cz.jl (N = 200, t0 = 14.32, amplitude error)."""
+    import torch
+    import robustgrape_b200 as rg
+    from robustgrape_b200 import rydberg_tools as rt
+    from robustgrape_b200._lib import Context
+    from robustgrape_b200.unitary_calculations import device_problem
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(0)
+    ctx = Context(0)
+    N, t0, nerr = (500, 7.613, 0) if args.workload == "C1" else (200, 14.32, 1)
+    srcs = [rg.ErrorSource(rt.rydberg_amplitude_error())] if nerr else []
+    up = rg.UnitaryRobustGRAPEProblem(t0=t0, ntimes=N, ndim=5, H0=rt.rydberg_h0(), nb_additional_param=1, error_sources=srcs)
+    fp = rg.FidelityRobustGRAPEProblem(up, np.diag([1.0, 2, 1, 0, 0]), rt.cz_target())
+    x = 2 * np.pi * np.random.default_rng(43).random(N + 1)
+    dp = device_problem(fp, ctx)
+    for _ in range(max(3, args.warmup)):
+        out = rg.calculate_fidelity_and_derivatives(fp, x, ctx=ctx)
+    l0 = ctx.launch_count
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        out = rg.calculate_fidelity_and_derivatives(fp, x, ctx=ctx)
+    dt = (time.perf_counter() - t) / args.steps
+    launches = ctx.launch_count - l0
+    line = {"metric": "GRAPE fidelity+derivatives evals/sec (CZ, single pulse)", "value": 1.0 / dt, "unit": "evals/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: one pulse, d=5 symmetric-blockaded Rydberg, N={N}, t0={t0}, e={nerr}; reference-signature call "
+                                   "calculate_fidelity_and_derivatives with host buffers (all four outputs returned)",
+                       "note": "latency bound: one fused-kernel launch per role plus the host call, the copies and a synchronisation"},
+            "e2e": {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": int((N + 1) * 8),
+                    "d2h_bytes_per_step": int((1 + (N + 1) + nerr + nerr * (N + 1)) * 8)},
+            "gpu_launches": int(launches), "path": dp.path(N + 1), "F": float(out[0])}
+    if not args.no_cpu_baseline:
+        from oracle import cpu_port
+        pp = cpu_port.PortProblem(fp)
+        X1 = x[:, None]
+        pp.fidelity_and_derivatives_batch(X1, 1)
+        t = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            pp.fidelity_and_derivatives_batch(X1, 1)
+        ct = (time.perf_counter() - t) / reps
+        line["cpu_baseline"] = {"value": 1.0 / ct, "unit": "evals/s", "cores": 1, "kind": "port",
+                                "sample": "the same pulse, C++ port of the reference's literal algorithm on one host thread"}
+    emit(line)
+
+
 def run_response(args):
     """--workload C3 (BASELINE.json configs[2]): fidelity-response sweep over a 4096-point frequency grid (N = 500, amplitude + frequency
     error sources, examples/time_optimal_cz.jl:60-67,82), the grid sharded over the ranks (no exchange inside a shard), rows all-gathered."""
@@ -428,7 +479,7 @@ def main():
     ap.add_argument("--cpu-pulses-per-thread", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16", "d32", "d48", "C3"],
+    ap.add_argument("--workload", default="C4", choices=["C4", "C5", "d16", "d32", "d48", "C3", "C1", "C2"],
                     help="C4 (default): multi-start CZ batch, the headline; C5 / d16 / d32 / d48: dense synthetic problem (d = 64 / 16 / 32 / 48) on the DMMA path (1 GPU)")
     ap.add_argument("--dense-ntimes", type=int, default=10000)
     ap.add_argument("--dense-norm", type=float, default=2.4, help="max_k ||dt H(k)||_1 of the dense workload (SURVEY 8d: 2.1 ... 5.4)")
@@ -451,6 +502,9 @@ def main():
         return
     if args.workload == "C3":
         run_response(args)
+        return
+    if args.workload in ("C1", "C2"):
+        run_single_pulse(args)
         return
     if args.workload != "C4":
         run_dense(args)
