@@ -801,9 +801,11 @@ def main():
             extra = dict(extra or {})
             extra["device_lbfgs"] = {"pulses": Bs, "iterations": info["iterations"], "evaluations": info["evaluations"], "seconds": dt,
                                      "evals_per_s_inside_optimiser": info["evaluations"] * Bs / dt,
+                                     "pulse_iterations_per_s": float(np.sum(its)) / dt,
                                      "median_infidelity_after": float(torch.median(dco).item()),
-                                     "note": "rg_lbfgs_batch_dev: iterates, gradients and curvature history stay in HBM; only a 12-byte "
-                                             "progress record per line-search round crosses PCIe (vs 131 MB per evaluation through the host API)"}
+                                     "note": "rg_lbfgs_batch_dev: iterates, gradients and curvature history stay in HBM; only a 16-byte "
+                                             "progress record per round crosses PCIe (vs 131 MB per evaluation through the host API); every "
+                                             "pulse runs its own line-search state machine, one batched evaluation per round"}
             del dXo, dco
         except Exception as ex:      # noqa: BLE001
             extra = dict(extra or {})

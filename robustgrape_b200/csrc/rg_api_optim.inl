@@ -76,7 +76,7 @@ extern "C" int rg_lbfgs_batch_dev(rg_problem* pr, int32_t B, double* dX, const d
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t nx = pr->dp.nx, m = history;
     const size_t nd = (size_t)B * nx * 5 + 2 * (size_t)B * m * nx + (size_t)B * m + (size_t)B * 4;       // doubles
-    const size_t ni = (size_t)B * 5 + 4;
+    const size_t ni = (size_t)B * 6 + 4;
     if (pr->lbfgs.ensure(nd * 8 + ni * 4)) RG_FAIL(ctx, RG_ERR_NOMEM, "L-BFGS state allocation failed (%zu MB)", (nd * 8) >> 20);
     double* q = pr->lbfgs.as<double>();
     LbfgsState st;
@@ -87,33 +87,34 @@ extern "C" int rg_lbfgs_batch_dev(rg_problem* pr, int32_t B, double* dX, const d
     st.S = q; q += (size_t)B * m * nx; st.Y = q; q += (size_t)B * m * nx; st.rho = q; q += (size_t)B * m;
     st.Ft = q; q += B; st.alpha = q; q += B; st.gd = q; q += 2 * (size_t)B;
     int* qi = reinterpret_cast<int*>(q);
-    st.hist = qi; st.head = qi + B; st.active = qi + 2 * B; st.done = qi + 3 * B; st.iters = qi + 4 * B; st.counters = qi + 5 * B;
+    st.hist = qi; st.head = qi + B; st.active = qi + 2 * B; st.done = qi + 3 * B; st.iters = qi + 4 * B; st.lsr = qi + 5 * B;
+    st.counters = qi + 6 * B;
+    st.max_iters = iterations;
     cudaStream_t s = ctx->stream;
     CU(ctx, cudaMemsetAsync(qi, 0, ni * 4, s));
     int nev = 0, rc;
     const int max_ls = 8;
     rc = rg_cost_and_grad_batch_reg_dev(pr, B, st.X, err_coeff, reg_kind, reg_c1, reg_c2, st.F, st.G); ++nev;
     if (rc) return rc;
-    int h_cnt[3] = {0, 0, 0}, its = 0, ls_fail = 0;
-    for (int it = 0; it < iterations; ++it) {
-        k_lbfgs_direction<<<B, 256, 0, s>>>(st, g_tol, it == 0);
-        ctx->launches++;
-        for (int ls = 0; ls < max_ls; ++ls) {
-            k_lbfgs_trial<<<std::min(4 * ctx->sm_count, (int)(((size_t)B * nx + 255) / 256)), 256, 0, s>>>(st);
-            rc = rg_cost_and_grad_batch_reg_dev(pr, B, st.Xt, err_coeff, reg_kind, reg_c1, reg_c2, st.Ft, st.Gt); ++nev;
-            if (rc) return rc;
-            k_lbfgs_check<<<B, 256, 0, s>>>(st, ls, max_ls);
-            CU(ctx, cudaMemsetAsync(st.counters, 0, 2 * sizeof(int), s));
-            k_lbfgs_count<<<std::min(64, (B + 255) / 256), 256, 0, s>>>(st);
-            ctx->launches += 3;
-            CU(ctx, cudaMemcpyAsync(h_cnt, st.counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
-            CU(ctx, cudaStreamSynchronize(s));
-            if (h_cnt[0] == 0) break;
-        }
-        its = it + 1; ls_fail = h_cnt[2];
-        // pulses that converged are marked by k_lbfgs_direction of the next iteration; stop when none is open
-        if (h_cnt[1] == 0) break;
+    // One round = one batched evaluation.  Pulses whose last trial was accepted get a new direction, the others the next (shorter) step
+    // along theirs; nobody waits.  The host reads 16 bytes per round to learn whether any pulse is still open.
+    int h_cnt[4] = {0, 0, 0, 0};
+    const long long max_rounds = (long long)iterations * (max_ls + 1) + 1;
+    for (long long round = 0; iterations > 0 && round < max_rounds; ++round) {
+        k_lbfgs_direction<<<B, 256, 0, s>>>(st, g_tol);
+        k_lbfgs_trial<<<std::min(4 * ctx->sm_count, (int)(((size_t)B * nx + 255) / 256)), 256, 0, s>>>(st);
+        ctx->launches += 2;
+        rc = rg_cost_and_grad_batch_reg_dev(pr, B, st.Xt, err_coeff, reg_kind, reg_c1, reg_c2, st.Ft, st.Gt); ++nev;
+        if (rc) return rc;
+        k_lbfgs_check<<<B, 256, 0, s>>>(st, max_ls);
+        CU(ctx, cudaMemsetAsync(st.counters, 0, 2 * sizeof(int), s));
+        k_lbfgs_count<<<std::min(64, (B + 255) / 256), 256, 0, s>>>(st);
+        ctx->launches += 2;
+        CU(ctx, cudaMemcpyAsync(h_cnt, st.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        if (h_cnt[1] == 0) break;                          // every pulse converged, failed its line search or spent its iterations
     }
+    const int its = h_cnt[3], ls_fail = h_cnt[2];
     CU(ctx, cudaGetLastError());
     if (iters_out) CU(ctx, cudaMemcpyAsync(iters_out, st.iters, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (info_out) { info_out[0] = nev; info_out[1] = its; info_out[2] = ls_fail; }

@@ -676,7 +676,8 @@ def test_device_lbfgs_reaches_high_fidelity(gpu_ctx):
     F = rg.calculate_fidelity_and_derivatives_batch(fp, X, want_grad=False)[0]
     assert np.median(1 - F) < 1e-6, (np.sort(1 - F), info)
     assert (1 - F < 1e-6).mean() >= 0.75, (np.sort(1 - F), info)
-    assert info["evaluations"] <= 1 + 8 * info["iterations"] and info["iterations"] <= 200, info
+    # one evaluation per round; a pulse needs at most 8 trials per iteration (plus 8 for a final failed search)
+    assert info["evaluations"] <= 9 + 8 * info["iterations"] and info["iterations"] <= 200, info
     # the single-pulse wrapper with the device optimiser
     prm = rg.FidelityRobustGRAPEParameters(x_initial=X0[:, 0], regularization_functions=[R.regularization_cost_phase_sin2],
                                            regularization_coeff1=[1e-6], regularization_coeff2=[1e-6], error_source_coeff=[], iterations=200,
