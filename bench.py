@@ -632,12 +632,12 @@ def main():
             sampler.__enter__()
         for _ in range(warmup):
             step()
-        t_spin = time.perf_counter()
-        while sample_clocks and time.perf_counter() - t_spin < 0.15:      # keep the GPU loaded until the barrier (untimed)
-            for _ in range(16):
-                step()
-            drain()
-            ctx.synchronize()
+        if sample_clocks:                                                  # keep the GPU loaded until the barrier (untimed); a fixed count,
+            for _ in range(16):                                            # so that every rank issues the same collectives with --gather nccl
+                for _ in range(16):
+                    step()
+                drain()
+                ctx.synchronize()
         drain()
         ctx.synchronize()
         barrier()
