@@ -533,6 +533,9 @@ struct FQDiag {
 #define RG_FQC_CTAS 4         // phase-only class, fidelity role.  Measured on B200 (C4, 8192 x 1000): 4 CTAs/SM (128 registers, 8 B of
                               // spills) 0.193 ms, 5 CTAs 0.200, 6 CTAs (80 registers, 240 B) 0.258, 8 CTAs 0.417; 7-level model 0.274 / 0.350 / 0.515
 #endif
+#ifndef RG_FQC_ERR_CTAS3
+#define RG_FQC_ERR_CTAS3 2    // phase-only class, error role, three blocks (7-level model): 2 CTAs/SM 0.418 ms, 3 CTAs/SM (spills) 0.475 ms
+#endif
 #ifndef RG_FQC_ERR_CTAS
 #define RG_FQC_ERR_CTAS 3     // phase-only class, error role: 3 CTAs/SM (168 registers) 0.334 ms, 4 (128) 0.357, 2 (192) 0.390, 5 0.480
 #endif
@@ -541,7 +544,7 @@ struct FQDiag {
 // ERR = true : role of error source e = blockIdx.y.  Fout[b*ne + e] = F_d2err[e];  out[(b*ne+e)*nx + ...] = dF_d2err[e]/dx
 // PC = true: phase-only drive class (constants from k_fqc_consts in P.pc_consts, one sincos per step and sweep).
 template <int D, unsigned UMASK, bool ERR, bool DA, bool PC = false>
-__global__ void __launch_bounds__(128, PC ? (ERR ? RG_FQC_ERR_CTAS : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
+__global__ void __launch_bounds__(128, PC ? (ERR ? (b2_nblocks(D, UMASK) >= 3 ? RG_FQC_ERR_CTAS3 : RG_FQC_ERR_CTAS) : RG_FQC_CTAS) : (ERR ? 2 : RG_FQ_CTAS))
 k_fused_q(const __grid_constant__ DevProblem P, const TriPlanDev tp, const double* __restrict__ X, int B, int wpp, int L, double* __restrict__ Fout,
           int fmode, double* __restrict__ out, double scale0, double scale0T, int do_grad, int use_xs, const PeerOut po,
           const FQAccum ac, int* __restrict__ status) {
